@@ -1,0 +1,144 @@
+/*
+ * mmdfn_b200 -- C ABI of the B200 (sm_100a) implementation of MM-DFN's per-dialogue
+ * forward/backward hot path.
+ *
+ * The reference (zerohd4869/MM-DFN) has no FFI / plugin layer: its boundary is the Python
+ * nn.Module API.  Each entry point below therefore replaces a group
+ * of ATen library calls at the cited reference lines (paths relative to the reference
+ * root); the Python drop-in modules under mm-dfn_b200/dropin/ bind them with ctypes
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 row-major contiguous data unless stated
+ *     (int = int32, long long = int64, unsigned char = keep-mask bytes);
+ *   - the caller (PyTorch) owns every input, output, saved-for-backward and workspace
+ *     buffer; nothing is allocated or freed here and there is no hidden global state;
+ *   - `stream` is a cudaStream_t; calls only enqueue work on it (asynchronous, re-entrant,
+ *     CUDA-graph capturable);
+ *   - return 0 on success, a positive cudaError_t value on a CUDA failure, a negative
+ *     MMDFN_E* value on an argument error.  There is no CPU fallback.
+ *   - node order of every (3N, .) array is the reference's stack [a; v; l]
+ *     (code/model_mm.py:98); dialogue i owns rows dia_off[i] .. dia_off[i+1]-1 of each third.
+ */
+#ifndef MMDFN_B200_H_
+#define MMDFN_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMDFN_EINVAL (-1)
+#define MMDFN_ENULL (-2)
+#define MMDFN_ERANGE (-3)
+
+/* Library identification: returns the ABI version (1). */
+int mmdfn_abi_version(void);
+
+/* ---- k1 + every dense contraction --------------------------------------------------------
+ * C[M,N] = act(alpha * op(A) op(B) + beta * C + bias[N]); op(A)(m,k) = transA ? A[k*lda+m] : A[m*lda+k];
+ * op(B)(k,n) = transB ? B[n*ldb+k] : B[k*ldb+n]; act: 0 none, 1 ReLU.  transA && transB unsupported.
+ * Replaces nn.Linear / torch.mm: code/model.py:1065,1094,1129,1337 ; code/model_GCN.py:186,454. */
+int mmdfn_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
+               const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int act,
+               void* stream);
+/* out[n] = beta*out[n] + sum_m A[m*lda+n]   (bias gradients) */
+int mmdfn_colsum(int M, int N, const float* A, long long lda, float beta, float* out, void* stream);
+
+/* ---- k2: nn.GRU(200,100,num_layers=2,bidirectional=True), no packing, h0 = 0 -------------------
+ * code/model.py:866 (lstm_l), :868 (rnn_parties); forward calls :1132, :1082, :1113, :1146.
+ * x: (rows, 200) row table.  rowmap == NULL: rows == T*nseq and slot (t,s) reads row t*nseq+s.
+ * rowmap (T, nseq) int32: slot reads row rowmap[t,s], -1 = all-zero input (speaker-party gather,
+ * fused).  w: 16 pointers in nn.GRU state_dict order {weight_ih, weight_hh, bias_ih, bias_hh} x
+ * {l0, l0_reverse, l1, l1_reverse}.  mask (T,nseq,200): inter-layer dropout keep mask or NULL.
+ * y2: (T, nseq, 200).  ws: mmdfn_bigru2_ws_floats() floats, kept for the backward. */
+long long mmdfn_bigru2_ws_floats(int T, int nseq, long long rows);
+int mmdfn_bigru2_fwd(int T, int nseq, long long rows, const float* x, const int* rowmap, const float* const* w,
+                     const unsigned char* mask, float mask_scale, float* y2, float* ws, void* stream);
+long long mmdfn_bigru2_bwd_ws_floats(int T, int nseq, long long rows);
+/* dx (rows,200): "=" or "+=" (accumulate_dx), may be NULL; dw: 16 gradient pointers ("="). */
+int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x, const int* rowmap, const float* const* w,
+                     const unsigned char* mask, float mask_scale, const float* y2, const float* dy2,
+                     const float* ws_fwd, float* dx, int accumulate_dx, float* const* dw, float* ws, void* stream);
+
+/* ---- k3/k4: speaker-party partition + fused scatter/combine/ragged pack ------------------------
+ * code/model.py:1070-1090, 1101-1121, 1134-1154 and simple_batch_graphify :553-565.
+ * qmask (T,B,S).  pos (T,B,S): rank of t among the non-zero entries of qmask[:,b,p] or -1;
+ * cnt (B,S); sel (T,B): last p with qmask != 0 or -1; rowmap (T, 3*B*S) or NULL: row of the
+ * stacked projection table (3,T,B,200) feeding slot (k, (m*B+b)*S+p).  Integer outputs are
+ * bit-exact w.r.t. torch.nonzero ordering. */
+int mmdfn_spk_partition(int T, int B, int S, const float* qmask, int* pos, int* cnt, int* sel, int* rowmap,
+                        void* stream);
+/* X[(m*N + dia_off[b] + t), :] = base_m[t,b,:] + w_m * Q[pos[t,b,sel], (m*B+b)*S+sel, :]  for t < L_b.
+ * Q (T, 3*B*S, 200) may be NULL (use_crn_speaker off). */
+int mmdfn_party_pack_fwd(int T, int B, int S, int N, const int* dia_off, const int* sel, const int* pos,
+                         const float* base_a, const float* base_v, const float* base_l, const float* Q, float wa,
+                         float wv, float wl, float* X, void* stream);
+int mmdfn_party_pack_bwd(int T, int B, int S, int N, const int* dia_off, const int* sel, const int* pos,
+                         const float* dX, float wa, float wv, float wl, float* dbase_a, float* dbase_v,
+                         float* dbase_l, float* dQ, void* stream);
+
+/* ---- k5: MM_GCN.create_big_adj in block-compact form (code/model_mm.py:122-180) ---------------
+ * blk_off (B+1) int64: float offset of dialogue b's 3 blocks (3*L_b^2 floats each dialogue).
+ * adj_blk: sum_b 3 L_b^2; adj_diag (3,N) pairs (a,v),(a,l),(v,l); dinv, rinv (3N); cos_blk, cos_diag
+ * saved for the backward; deg_ws (3N) scratch. */
+int mmdfn_adj_fwd(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* X,
+                  float modal_weight, float* adj_blk, float* adj_diag, float* dinv, float* rinv, float* cos_blk,
+                  float* cos_diag, float* deg_ws, void* stream);
+/* d_blk / d_diag: gradient w.r.t. the stored entries (d_blk is clobbered).  dX = add + grad (add may be NULL). */
+int mmdfn_adj_bwd(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* X,
+                  float modal_weight, const float* adj_blk, const float* adj_diag, const float* dinv,
+                  const float* rinv, const float* cos_blk, const float* cos_diag, float* d_blk, const float* d_diag,
+                  const float* add, float* dX, float* dd_ws, void* stream);
+/* dense (3N,3N) materialisation for callers that want the reference's tensor (not on the hot path) */
+int mmdfn_adj_densify(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* adj_blk,
+                      const float* adj_diag, float* dense, void* stream);
+
+/* ---- k6: message aggregate y = A_hat x, x,y (3N,G)  (torch.spmm, code/model_GCN.py:178) -------- */
+int mmdfn_adj_spmm(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* adj_blk,
+                   const float* adj_diag, const float* x, int G, float* y, void* stream);
+/* d_blk[r,j] (+)= dhi_r . z_j ; d_diag[p][n] (+)= both orientations */
+int mmdfn_adj_grad(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* dhi,
+                   const float* z, int G, float* d_blk, float* d_diag, int accumulate, void* stream);
+
+/* ---- k6/k7/k8: GCNII_lyc stack (code/model_GCN.py:444-488, GraphConvolution :176-189, LSTM :466)
+ * X (3N,200) -> F (3N,300) = [dropout(X) | z_K].  convW: K pointers to (200,100).  masks: keep bytes
+ * (3N,200), (3N,100), (K,3N,100) or NULL. */
+long long mmdfn_gcn_stack_ws_floats(int n3, int K);
+int mmdfn_gcn_stack_fwd(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* adj_blk,
+                        const float* adj_diag, const float* X, int K, int reason_flag, double lamda, double alpha,
+                        const float* W0, const float* b0, const float* const* convW, const float* w_ih,
+                        const float* w_hh, const float* b_ih, const float* b_hh, const unsigned char* mask_x,
+                        const unsigned char* mask_h0, const unsigned char* mask_layers, float mask_scale, float* F,
+                        float* ws, void* stream);
+long long mmdfn_gcn_stack_bwd_ws_floats(int n3);
+int mmdfn_gcn_stack_bwd(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* adj_blk,
+                        const float* adj_diag, int K, int reason_flag, double lamda, double alpha, const float* W0,
+                        const float* const* convW, const float* w_ih, const float* w_hh,
+                        const unsigned char* mask_x, const unsigned char* mask_h0, const unsigned char* mask_layers,
+                        float mask_scale, const float* F, const float* ws_fwd, const float* dF, float* dX,
+                        float* d_adj_blk, float* d_adj_diag, float* dW0, float* db0, float* const* dconvW,
+                        float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, float* ws, void* stream);
+
+/* ---- k9: head + loss (code/model.py:1328-1337 ; code/loss.py:14-34) ---------------------------
+ * F (3N,300); mask (N,900) keep bytes or NULL; Wc (C,900); R (3N,300) saved; log_prob (N,C). C <= 16. */
+int mmdfn_head_fwd(int N, int C, const float* F, const unsigned char* mask, float mask_scale, const float* Wc,
+                   const float* bc, float* R, float* log_prob, void* stream);
+int mmdfn_head_bwd(int N, int C, const unsigned char* mask, float mask_scale, const float* Wc, const float* R,
+                   const float* log_prob, const float* dlog_prob, float* dF, float* dWc, float* dbc,
+                   float* dlogits_ws, void* stream);
+int mmdfn_focal_loss_fwd(int N, int C, const float* log_prob, const long long* target, const float* alpha,
+                         float gamma, int size_average, float* loss, void* stream);
+int mmdfn_focal_loss_bwd(int N, int C, const float* log_prob, const long long* target, const float* alpha,
+                         float gamma, int size_average, const float* dloss, float* dlog_prob, void* stream);
+
+/* ---- support: dropout keep masks, fused flat-buffer Adam(+L2) (code/run_train_erc.py:512) ----- */
+int mmdfn_dropout_mask(long long n, float p, unsigned long long seed, unsigned long long offset,
+                       unsigned char* mask, void* stream);
+int mmdfn_adam_step(long long n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMDFN_B200_H_ */

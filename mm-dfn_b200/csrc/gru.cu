@@ -1,0 +1,350 @@
+// k2/k3: persistent GRU recurrence (forward + backward) and the 2-layer bidirectional
+// orchestrator that replaces nn.GRU(200,100,num_layers=2,bidirectional=True)
+// ("lstm_l" code/model.py:866,1132 and the shared "rnn_parties" :868,1082,1113,1146).
+//
+// Design: the input-gate GEMM is hoisted out of the time loop (one dense GEMM per layer
+// over all rows).  One CTA owns NB sequences of one direction for the whole sequence:
+// each of 300 threads keeps one row of W_hh (100 floats) in registers, the NB hidden
+// states live in shared memory and are read as broadcast 128-bit loads, so the T-step
+// loop touches HBM only for the per-step gate rows (coalesced, prefetched before the
+// mat-vec) and the outputs.  For the speaker-party encoder the per-step rows are fetched
+// through `rowmap` (gather fused into the recurrence): the projected utterance table is
+// multiplied by W_ih once per utterance instead of once per (speaker, position) slot.
+#include "internal.cuh"
+#include "../../include/mmdfn_b200.h"
+
+namespace mmdfn {
+
+constexpr int GH = 100;          // hidden size (D_e), fixed by the reference (code/run_train_erc.py:389)
+constexpr int G3 = 300;
+constexpr int GRU_THREADS = 320;
+
+struct GruFwdArgs {
+  int T, nseq;
+  const float* xg;        // (rows, 600): [dir0: r z n | dir1: r z n], bias_ih included
+  const int* rowmap;      // (T, nseq) row of xg per slot, -1 = zero input; nullptr = identity
+  const float* b_ih[2];   // used for rowmap == -1 slots
+  const float* w_hh[2];   // (300, 100)
+  const float* b_hh[2];   // (300)
+  float* y;               // (T, nseq, 200) [fwd | bwd]
+  float* gates;           // (T, nseq, 2, 400) r z n hn, nullable
+};
+
+template <int NB>
+__global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(GruFwdArgs p) {
+  __shared__ __align__(16) float hs[NB][GH];
+  __shared__ __align__(16) float pre[NB][4 * GH];
+  const int tid = threadIdx.x;
+  const int dir = blockIdx.y;
+  const int s0 = blockIdx.x * NB;
+  const int nb = min(NB, p.nseq - s0);
+  const int j = tid < G3 ? tid : G3 - 1;     // threads 300..319 only help in the pointwise phase
+  float w[GH];
+  {
+    const float* wr = p.w_hh[dir] + (i64)j * GH;
+#pragma unroll
+    for (int k = 0; k < GH; k++) w[k] = wr[k];
+  }
+  const float bh = p.b_hh[dir][j];
+  const float bi = p.b_ih[dir] ? p.b_ih[dir][j] : 0.f;
+  for (int i = tid; i < NB * GH; i += GRU_THREADS) (&hs[0][0])[i] = 0.f;
+  __syncthreads();
+
+  for (int step = 0; step < p.T; step++) {
+    const int t = dir ? (p.T - 1 - step) : step;
+    float xv[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      xv[b] = 0.f;
+      if (b < nb) {
+        const i64 slot = (i64)t * p.nseq + s0 + b;
+        const i64 row = p.rowmap ? (i64)p.rowmap[slot] : slot;
+        xv[b] = row >= 0 ? p.xg[row * 600 + dir * G3 + j] : bi;
+      }
+    }
+    float acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) acc[b] = bh;
+#pragma unroll
+    for (int k = 0; k < GH; k += 4) {
+#pragma unroll
+      for (int b = 0; b < NB; b++) {
+        const float4 h4 = *reinterpret_cast<const float4*>(&hs[b][k]);
+        acc[b] = fmaf(w[k], h4.x, acc[b]);
+        acc[b] = fmaf(w[k + 1], h4.y, acc[b]);
+        acc[b] = fmaf(w[k + 2], h4.z, acc[b]);
+        acc[b] = fmaf(w[k + 3], h4.w, acc[b]);
+      }
+    }
+    if (tid < G3) {
+#pragma unroll
+      for (int b = 0; b < NB; b++) {
+        if (tid < 2 * GH) {
+          pre[b][tid] = xv[b] + acc[b];
+        } else {
+          pre[b][tid] = xv[b];
+          pre[b][tid + GH] = acc[b];
+        }
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nb * GH; idx += GRU_THREADS) {
+      const int b = idx / GH, u = idx - b * GH;
+      const float r = sigmoidf_(pre[b][u]);
+      const float z = sigmoidf_(pre[b][GH + u]);
+      const float hn = pre[b][3 * GH + u];
+      const float n = tanhf(pre[b][2 * GH + u] + r * hn);
+      const float hnew = (1.0f - z) * n + z * hs[b][u];
+      hs[b][u] = hnew;
+      const i64 slot = (i64)t * p.nseq + s0 + b;
+      p.y[slot * 200 + dir * GH + u] = hnew;
+      if (p.gates) {
+        float* g = p.gates + (slot * 2 + dir) * 400;
+        g[u] = r; g[GH + u] = z; g[2 * GH + u] = n; g[3 * GH + u] = hn;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+struct GruBwdArgs {
+  int T, nseq;
+  const float* dy;      // (T, nseq, 200)
+  const float* y;       // (T, nseq, 200)
+  const float* gates;   // (T, nseq, 2, 400)
+  const float* w_hh[2];
+  float* dxg;           // (T, nseq, 2, 300)  d/d(input gates)  = [dr_pre dz_pre dn_pre]
+  float* dhn;           // (T, nseq, 2, 100)  d/d(W_hn h + b_hn) = dn_pre * r
+};
+
+template <int NB>
+__global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(GruBwdArgs p) {
+  __shared__ __align__(16) float dh[NB][GH];
+  __shared__ __align__(16) float dgh[NB][G3];
+  __shared__ __align__(16) float part[3][NB][GH];
+  const int tid = threadIdx.x;
+  const int dir = blockIdx.y;
+  const int s0 = blockIdx.x * NB;
+  const int nb = min(NB, p.nseq - s0);
+  const int u_mv = tid % GH;
+  const int jp = tid < G3 ? tid / GH : 2;
+  float w[GH];   // w[jj] = W_hh[jp*100 + jj][u]  (a column slice: computes W_hh^T dgh)
+#pragma unroll
+  for (int jj = 0; jj < GH; jj++) w[jj] = p.w_hh[dir][(i64)(jp * GH + jj) * GH + u_mv];
+  for (int i = tid; i < NB * GH; i += GRU_THREADS) (&dh[0][0])[i] = 0.f;
+  for (int i = tid; i < 3 * NB * GH; i += GRU_THREADS) (&part[0][0][0])[i] = 0.f;
+  for (int i = tid; i < NB * G3; i += GRU_THREADS) (&dgh[0][0])[i] = 0.f;
+  __syncthreads();
+
+  for (int step = 0; step < p.T; step++) {
+    const int t = dir ? step : (p.T - 1 - step);       // reverse of the forward visiting order
+    const int tp = dir ? t + 1 : t - 1;                // slot that produced h_prev
+    for (int idx = tid; idx < nb * GH; idx += GRU_THREADS) {
+      const int b = idx / GH, u = idx - b * GH;
+      const i64 slot = (i64)t * p.nseq + s0 + b;
+      const float* g = p.gates + (slot * 2 + dir) * 400;
+      const float r = g[u], z = g[GH + u], n = g[2 * GH + u], hn = g[3 * GH + u];
+      const float hp = (tp >= 0 && tp < p.T) ? p.y[((i64)tp * p.nseq + s0 + b) * 200 + dir * GH + u] : 0.f;
+      const float dht = dh[b][u] + part[0][b][u] + part[1][b][u] + part[2][b][u] + p.dy[slot * 200 + dir * GH + u];
+      const float dn = dht * (1.0f - z);
+      const float dz = dht * (hp - n);
+      const float dn_pre = dn * (1.0f - n * n);
+      const float dz_pre = dz * z * (1.0f - z);
+      const float dr_pre = dn_pre * hn * r * (1.0f - r);
+      const float dhn_ = dn_pre * r;
+      float* o = p.dxg + (slot * 2 + dir) * G3;
+      o[u] = dr_pre; o[GH + u] = dz_pre; o[2 * GH + u] = dn_pre;
+      p.dhn[(slot * 2 + dir) * GH + u] = dhn_;
+      dgh[b][u] = dr_pre; dgh[b][GH + u] = dz_pre; dgh[b][2 * GH + u] = dhn_;
+      dh[b][u] = dht * z;
+    }
+    __syncthreads();
+    float acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) acc[b] = 0.f;
+#pragma unroll
+    for (int k = 0; k < GH; k += 4) {
+#pragma unroll
+      for (int b = 0; b < NB; b++) {
+        const float4 d4 = *reinterpret_cast<const float4*>(&dgh[b][jp * GH + k]);
+        acc[b] = fmaf(w[k], d4.x, acc[b]);
+        acc[b] = fmaf(w[k + 1], d4.y, acc[b]);
+        acc[b] = fmaf(w[k + 2], d4.z, acc[b]);
+        acc[b] = fmaf(w[k + 3], d4.w, acc[b]);
+      }
+    }
+    if (tid < G3) {
+#pragma unroll
+      for (int b = 0; b < NB; b++) part[jp][b][u_mv] = acc[b];
+    }
+    __syncthreads();
+  }
+}
+
+// dG[rowmap[slot]] += dxg[slot]  (600 floats per slot); dG pre-zeroed
+__global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ rowmap, i64 nslots,
+                                    float* __restrict__ dst) {
+  const i64 slot = (i64)blockIdx.x * 4 + threadIdx.y;
+  if (slot >= nslots) return;
+  const int row = rowmap[slot];
+  if (row < 0) return;
+  for (int c = threadIdx.x; c < 600; c += 32) atomicAdd(dst + (i64)row * 600 + c, src[slot * 600 + c]);
+}
+
+// y = x * mask * scale (uint8 mask); in == out allowed
+__global__ void mask_mul_kernel(const float* __restrict__ x, const unsigned char* __restrict__ m, float scale, i64 n,
+                                float* __restrict__ y) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = m[i] ? x[i] * scale : 0.f;
+}
+
+static int launch_gru_fwd(const GruFwdArgs& a, cudaStream_t st) {
+  if (a.T <= 0 || a.nseq <= 0) return 0;
+  // few sequences: smaller tiles -> more CTAs and a shorter per-step critical path
+  if ((i64)ceil_div(a.nseq, 8) * 2 >= 148) {
+    gru_fwd_kernel<8><<<dim3(ceil_div(a.nseq, 8), 2), GRU_THREADS, 0, st>>>(a);
+  } else {
+    gru_fwd_kernel<4><<<dim3(ceil_div(a.nseq, 4), 2), GRU_THREADS, 0, st>>>(a);
+  }
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_gru_bwd(const GruBwdArgs& a, cudaStream_t st) {
+  if (a.T <= 0 || a.nseq <= 0) return 0;
+  if ((i64)ceil_div(a.nseq, 8) * 2 >= 148) {
+    gru_bwd_kernel<8><<<dim3(ceil_div(a.nseq, 8), 2), GRU_THREADS, 0, st>>>(a);
+  } else {
+    gru_bwd_kernel<4><<<dim3(ceil_div(a.nseq, 4), 2), GRU_THREADS, 0, st>>>(a);
+  }
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mmdfn
+
+using namespace mmdfn;
+
+// Weight pointer table order (16 entries), matching nn.GRU's state_dict names:
+//   [0..3]  weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0
+//   [4..7]  the same with suffix _reverse
+//   [8..11] *_l1      [12..15] *_l1_reverse
+extern "C" long long mmdfn_bigru2_ws_floats(int T, int nseq, long long rows) {
+  const i64 slots = (i64)T * nseq;
+  // xg1 (rows*600) | y1 (slots*200) | y1d (slots*200) | gates1 (slots*800) | xg2 (slots*600) | gates2 (slots*800)
+  return rows * 600 + slots * (200 + 200 + 800 + 600 + 800);
+}
+
+extern "C" int mmdfn_bigru2_fwd(int T, int nseq, long long rows, const float* x, const int* rowmap,
+                                const float* const* w, const unsigned char* mask, float mask_scale, float* y2,
+                                float* ws, void* stream) {
+  if (!x || !w || !y2 || !ws) return MMDFN_ENULL;
+  if (T < 0 || nseq < 0 || rows < 0) return MMDFN_EINVAL;
+  if (!rowmap && rows != (i64)T * nseq) return MMDFN_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const i64 slots = (i64)T * nseq;
+  if (slots == 0) return 0;
+  float* xg1 = ws;
+  float* y1 = xg1 + rows * 600;
+  float* y1d = y1 + slots * 200;
+  float* gates1 = y1d + slots * 200;
+  float* xg2 = gates1 + slots * 800;
+  float* gates2 = xg2 + slots * 600;
+  if (rows > 2000000000LL / 600 || slots > 2000000000LL / 1) return MMDFN_ERANGE;
+  // layer 0 input gates for both directions
+  MMDFN_TRY(gemm(false, true, (int)rows, 300, 200, 1.f, x, 200, w[0], 200, 0.f, xg1, 600, w[2], 0, st));
+  MMDFN_TRY(gemm(false, true, (int)rows, 300, 200, 1.f, x, 200, w[4], 200, 0.f, xg1 + 300, 600, w[6], 0, st));
+  GruFwdArgs a{T, nseq, xg1, rowmap, {w[2], w[6]}, {w[1], w[5]}, {w[3], w[7]}, y1, gates1};
+  MMDFN_TRY(launch_gru_fwd(a, st));
+  const float* l1in = y1;
+  if (mask) {
+    mask_mul_kernel<<<(unsigned)ceil_div64(slots * 200, 256), 256, 0, st>>>(y1, mask, mask_scale, slots * 200, y1d);
+    MMDFN_LAUNCH_CHECK();
+    l1in = y1d;
+  }
+  MMDFN_TRY(gemm(false, true, (int)slots, 300, 200, 1.f, l1in, 200, w[8], 200, 0.f, xg2, 600, w[10], 0, st));
+  MMDFN_TRY(gemm(false, true, (int)slots, 300, 200, 1.f, l1in, 200, w[12], 200, 0.f, xg2 + 300, 600, w[14], 0, st));
+  GruFwdArgs b{T, nseq, xg2, nullptr, {w[10], w[14]}, {w[9], w[13]}, {w[11], w[15]}, y2, gates2};
+  MMDFN_TRY(launch_gru_fwd(b, st));
+  return 0;
+}
+
+extern "C" long long mmdfn_bigru2_bwd_ws_floats(int T, int nseq, long long rows) {
+  const i64 slots = (i64)T * nseq;
+  // dxg (slots*600) | dhn (slots*200) | dy1 (slots*200) | dG (rows*600)
+  return slots * (600 + 200 + 200) + rows * 600;
+}
+
+// One layer's weight gradients from dxg/dhn.  xin: the layer input rows (ld 200) matching the
+// rows of dgate (ld 600); yl: that layer's output (T, nseq, 200).
+static int gru_layer_wgrads(int T, int nseq, i64 in_rows, const float* dgate_in, const float* xin, const float* dxg,
+                            const float* dhn, const float* yl, float* const* dw, int base, cudaStream_t st) {
+  const i64 slots = (i64)T * nseq;
+  const i64 mprev = (i64)(T - 1) * nseq;
+  for (int d = 0; d < 2; d++) {
+    float* dW_ih = dw[base + 4 * d + 0];
+    float* dW_hh = dw[base + 4 * d + 1];
+    float* db_ih = dw[base + 4 * d + 2];
+    float* db_hh = dw[base + 4 * d + 3];
+    // dW_ih (300,200) = dgate_in[:, d]^T xin
+    MMDFN_TRY(gemm(true, false, 300, 200, (int)in_rows, 1.f, dgate_in + d * 300, 600, xin, 200, 0.f, dW_ih, 200, nullptr, 0, st));
+    MMDFN_TRY(colsum((int)slots, 300, dxg + d * 300, 600, 0.f, db_ih, st));
+    // h_prev of slot t is y[t-1] (forward direction) / y[t+1] (reverse direction)
+    const float* A_rz = d == 0 ? dxg + (i64)nseq * 600 : dxg + 300;
+    const float* A_n = d == 0 ? dhn + (i64)nseq * 200 : dhn + 100;
+    const float* Bh = d == 0 ? yl : yl + (i64)nseq * 200 + 100;
+    MMDFN_TRY(gemm(true, false, 200, 100, (int)mprev, 1.f, A_rz, 600, Bh, 200, 0.f, dW_hh, 100, nullptr, 0, st));
+    MMDFN_TRY(gemm(true, false, 100, 100, (int)mprev, 1.f, A_n, 200, Bh, 200, 0.f, dW_hh + 200 * 100, 100, nullptr, 0, st));
+    MMDFN_TRY(colsum((int)slots, 200, dxg + d * 300, 600, 0.f, db_hh, st));
+    MMDFN_TRY(colsum((int)slots, 100, dhn + d * 100, 200, 0.f, db_hh + 200, st));
+  }
+  return 0;
+}
+
+extern "C" int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x, const int* rowmap,
+                                const float* const* w, const unsigned char* mask, float mask_scale, const float* y2,
+                                const float* dy2, const float* ws_fwd, float* dx, int accumulate_dx,
+                                float* const* dw, float* ws, void* stream) {
+  if (!x || !w || !y2 || !dy2 || !ws_fwd || !dw || !ws) return MMDFN_ENULL;
+  if (!rowmap && rows != (i64)T * nseq) return MMDFN_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const i64 slots = (i64)T * nseq;
+  if (slots == 0) return 0;
+  const float* xg1 = ws_fwd; (void)xg1;
+  const float* y1 = ws_fwd + rows * 600;
+  const float* y1d = y1 + slots * 200;
+  const float* gates1 = y1d + slots * 200;
+  const float* gates2 = gates1 + slots * 800 + slots * 600;
+  const float* l1in = mask ? y1d : y1;
+  float* dxg = ws;
+  float* dhn = dxg + slots * 600;
+  float* dy1 = dhn + slots * 200;
+  float* dG = dy1 + slots * 200;
+  // ---- layer 1 ----
+  GruBwdArgs b{T, nseq, dy2, y2, gates2, {w[9], w[13]}, dxg, dhn};
+  MMDFN_TRY(launch_gru_bwd(b, st));
+  MMDFN_TRY(gru_layer_wgrads(T, nseq, slots, dxg, l1in, dxg, dhn, y2, dw, 8, st));
+  MMDFN_TRY(gemm(false, false, (int)slots, 200, 300, 1.f, dxg, 600, w[8], 200, 0.f, dy1, 200, nullptr, 0, st));
+  MMDFN_TRY(gemm(false, false, (int)slots, 200, 300, 1.f, dxg + 300, 600, w[12], 200, 1.f, dy1, 200, nullptr, 0, st));
+  if (mask) {
+    mask_mul_kernel<<<(unsigned)ceil_div64(slots * 200, 256), 256, 0, st>>>(dy1, mask, mask_scale, slots * 200, dy1);
+    MMDFN_LAUNCH_CHECK();
+  }
+  // ---- layer 0 ----
+  GruBwdArgs a{T, nseq, dy1, y1, gates1, {w[1], w[5]}, dxg, dhn};
+  MMDFN_TRY(launch_gru_bwd(a, st));
+  const float* dgate_in = dxg;
+  if (rowmap) {
+    MMDFN_TRY(fill_zero(dG, (size_t)rows * 600 * sizeof(float), st));
+    scatter_rows_kernel<<<(unsigned)ceil_div64(slots, 4), dim3(32, 4), 0, st>>>(dxg, rowmap, slots, dG);
+    MMDFN_LAUNCH_CHECK();
+    dgate_in = dG;
+  }
+  MMDFN_TRY(gru_layer_wgrads(T, nseq, rows, dgate_in, x, dxg, dhn, y1, dw, 0, st));
+  if (dx) {
+    const float beta = accumulate_dx ? 1.f : 0.f;
+    MMDFN_TRY(gemm(false, false, (int)rows, 200, 300, 1.f, dgate_in, 600, w[0], 200, beta, dx, 200, nullptr, 0, st));
+    MMDFN_TRY(gemm(false, false, (int)rows, 200, 300, 1.f, dgate_in + 300, 600, w[4], 200, 1.f, dx, 200, nullptr, 0, st));
+  }
+  return 0;
+}

@@ -1,0 +1,214 @@
+// k9: classifier head (dropout -> ReLU -> Linear(900,C) -> log_softmax; code/model.py:1328-1337)
+// and FocalLoss (code/loss.py:14-34), forward + backward; plus the counter-based dropout
+// mask generator and the fused flat-buffer Adam(+L2) step used by the data-parallel trainer
+// (optim.Adam(lr, weight_decay=l2), code/run_train_erc.py:512).
+#include "internal.cuh"
+#include "../../include/mmdfn_b200.h"
+
+namespace mmdfn {
+
+constexpr int HF = 300;     // per-modality feature width [x200 | g100]
+constexpr int MAXC = 16;
+
+// R[(m*N+n), k] = relu(F[(m*N+n), k] * mask[n, m*300+k] * scale)
+__global__ void head_relu_kernel(int N, const float* __restrict__ F, const unsigned char* __restrict__ mask,
+                                 float scale, float* __restrict__ R) {
+  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (i64)3 * N * HF) return;
+  const i64 row = idx / HF;
+  const int k = (int)(idx - row * HF);
+  const int m = (int)(row / N);
+  const i64 n = row - (i64)m * N;
+  float v = F[idx];
+  if (mask) v = mask[n * 900 + m * HF + k] ? v * scale : 0.f;
+  R[idx] = fmaxf(v, 0.f);
+}
+
+// in-place row-wise log_softmax over C (thread per row)
+__global__ void log_softmax_kernel(int N, int C, const float* logits, float* out) {   // in place allowed
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* x = logits + (i64)n * C;
+  float mx = x[0];
+  for (int c = 1; c < C; c++) mx = fmaxf(mx, x[c]);
+  float s = 0.f;
+  for (int c = 0; c < C; c++) s += expf(x[c] - mx);
+  const float lse = mx + logf(s);
+  for (int c = 0; c < C; c++) out[(i64)n * C + c] = x[c] - lse;
+}
+
+// dlogits = dlp - exp(lp) * sum_c dlp
+__global__ void log_softmax_bwd_kernel(int N, int C, const float* __restrict__ lp, const float* __restrict__ dlp,
+                                       float* __restrict__ dlogits) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int c = 0; c < C; c++) s += dlp[(i64)n * C + c];
+  for (int c = 0; c < C; c++) dlogits[(i64)n * C + c] = dlp[(i64)n * C + c] - expf(lp[(i64)n * C + c]) * s;
+}
+
+// dF = dR * [R > 0] * (mask ? scale : 1), in place on dF
+__global__ void head_relu_bwd_kernel(i64 n, const float* __restrict__ R, float scale, float* __restrict__ dF) {
+  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  dF[idx] = R[idx] > 0.f ? dF[idx] * scale : 0.f;
+}
+
+// loss = (mean|sum)_n -(1-pt)^gamma * alpha[y] * lp[n,y],  pt = exp(lp[n,y]) (no gradient through pt)
+__global__ void focal_fwd_kernel(int N, int C, const float* __restrict__ lp, const long long* __restrict__ target,
+                                 const float* __restrict__ alpha, float gamma, float norm, float* __restrict__ loss) {
+  __shared__ float red[8];
+  float v = 0.f;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) {
+    const long long y = target[n];
+    const float l = lp[(i64)n * C + y];
+    const float a = alpha ? alpha[y] : 1.f;
+    const float w = gamma == 0.f ? 1.f : powf(1.f - expf(l), gamma);
+    v = -w * a * l * norm;
+  }
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(loss, v);
+  }
+}
+
+__global__ void focal_bwd_kernel(int N, int C, const float* __restrict__ lp, const long long* __restrict__ target,
+                                 const float* __restrict__ alpha, float gamma, float norm,
+                                 const float* __restrict__ dloss, float* __restrict__ dlp) {
+  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (i64)N * C) return;
+  const int n = (int)(idx / C), c = (int)(idx - (i64)n * C);
+  const long long y = target[n];
+  float g = 0.f;
+  if (c == y) {
+    const float l = lp[idx];
+    const float a = alpha ? alpha[y] : 1.f;
+    const float w = gamma == 0.f ? 1.f : powf(1.f - expf(l), gamma);
+    g = -w * a * norm * dloss[0];
+  }
+  dlp[idx] = g;
+}
+
+// counter-based keep mask: keep with probability 1-p; one 64-bit mix per element (splitmix64)
+__global__ void dropout_mask_kernel(i64 n, float p, unsigned long long seed, unsigned long long offset,
+                                    unsigned char* __restrict__ mask) {
+  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  unsigned long long z = seed * 0x9E3779B97F4A7C15ull + (offset + (unsigned long long)idx) * 0xD1342543DE82EF95ull;
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);   // [0,1)
+  mask[idx] = u >= p ? 1 : 0;
+}
+
+// Adam with L2 folded into the gradient (torch.optim.Adam weight_decay semantics), grads pre-scaled by gscale
+__global__ void adam_kernel(i64 n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, float lr, float beta1, float beta2, float eps, float wd,
+                            float bc1, float bc2_sqrt, float gscale) {
+  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const float w = p[idx];
+  const float gr = fmaf(wd, w, g[idx] * gscale);
+  const float mm = beta1 * m[idx] + (1.f - beta1) * gr;
+  const float vv = beta2 * v[idx] + (1.f - beta2) * gr * gr;
+  m[idx] = mm;
+  v[idx] = vv;
+  const float denom = sqrtf(vv) / bc2_sqrt + eps;
+  p[idx] = w - (lr / bc1) * (mm / denom);
+}
+
+}  // namespace mmdfn
+
+using namespace mmdfn;
+
+extern "C" int mmdfn_head_fwd(int N, int C, const float* F, const unsigned char* mask, float mask_scale,
+                              const float* Wc, const float* bc, float* R, float* log_prob, void* stream) {
+  if (!F || !Wc || !bc || !R || !log_prob) return MMDFN_ENULL;
+  if (C <= 0 || C > MAXC || N < 0) return MMDFN_EINVAL;
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  head_relu_kernel<<<(unsigned)ceil_div64((i64)3 * N * HF, 256), 256, 0, st>>>(N, F, mask, mask_scale, R);
+  MMDFN_LAUNCH_CHECK();
+  for (int m = 0; m < 3; m++)
+    MMDFN_TRY(gemm(false, true, N, C, HF, 1.f, R + (i64)m * N * HF, HF, Wc + m * HF, 3 * HF, m ? 1.f : 0.f, log_prob, C,
+                   m ? nullptr : bc, 0, st));
+  log_softmax_kernel<<<ceil_div(N, 128), 128, 0, st>>>(N, C, log_prob, log_prob);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
+// dlogits_ws: (N, C) scratch.  dF (3N,300), dWc (C,900), dbc (C) are overwritten.
+extern "C" int mmdfn_head_bwd(int N, int C, const unsigned char* mask, float mask_scale, const float* Wc,
+                              const float* R, const float* log_prob, const float* dlog_prob, float* dF, float* dWc,
+                              float* dbc, float* dlogits_ws, void* stream) {
+  if (!Wc || !R || !log_prob || !dlog_prob || !dF || !dWc || !dbc || !dlogits_ws) return MMDFN_ENULL;
+  if (C <= 0 || C > MAXC || N < 0) return MMDFN_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) {
+    MMDFN_TRY(fill_zero(dWc, (size_t)C * 900 * sizeof(float), st));
+    return fill_zero(dbc, (size_t)C * sizeof(float), st);
+  }
+  log_softmax_bwd_kernel<<<ceil_div(N, 128), 128, 0, st>>>(N, C, log_prob, dlog_prob, dlogits_ws);
+  MMDFN_LAUNCH_CHECK();
+  MMDFN_TRY(colsum(N, C, dlogits_ws, C, 0.f, dbc, st));
+  for (int m = 0; m < 3; m++) {
+    MMDFN_TRY(gemm(true, false, C, HF, N, 1.f, dlogits_ws, C, R + (i64)m * N * HF, HF, 0.f, dWc + m * HF, 3 * HF, nullptr, 0, st));
+    MMDFN_TRY(gemm(false, false, N, HF, C, 1.f, dlogits_ws, C, Wc + m * HF, 3 * HF, 0.f, dF + (i64)m * N * HF, HF, nullptr, 0, st));
+  }
+  head_relu_bwd_kernel<<<(unsigned)ceil_div64((i64)3 * N * HF, 256), 256, 0, st>>>((i64)3 * N * HF, R, mask ? mask_scale : 1.f, dF);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmdfn_focal_loss_fwd(int N, int C, const float* log_prob, const long long* target, const float* alpha,
+                                    float gamma, int size_average, float* loss, void* stream) {
+  if (!log_prob || !target || !loss) return MMDFN_ENULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  MMDFN_TRY(fill_zero(loss, sizeof(float), st));
+  if (N <= 0) return 0;
+  const float norm = size_average ? 1.0f / (float)N : 1.0f;
+  focal_fwd_kernel<<<ceil_div(N, 256), 256, 0, st>>>(N, C, log_prob, target, alpha, gamma, norm, loss);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmdfn_focal_loss_bwd(int N, int C, const float* log_prob, const long long* target, const float* alpha,
+                                    float gamma, int size_average, const float* dloss, float* dlog_prob,
+                                    void* stream) {
+  if (!log_prob || !target || !dloss || !dlog_prob) return MMDFN_ENULL;
+  if (N <= 0) return 0;
+  const float norm = size_average ? 1.0f / (float)N : 1.0f;
+  focal_bwd_kernel<<<(unsigned)ceil_div64((i64)N * C, 256), 256, 0, (cudaStream_t)stream>>>(N, C, log_prob, target, alpha, gamma,
+                                                                                    norm, dloss, dlog_prob);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmdfn_dropout_mask(long long n, float p, unsigned long long seed, unsigned long long offset,
+                                  unsigned char* mask, void* stream) {
+  if (!mask) return MMDFN_ENULL;
+  if (n <= 0) return 0;
+  dropout_mask_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(n, p, seed, offset, mask);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmdfn_adam_step(long long n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                               float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                               float grad_scale, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq) return MMDFN_ENULL;
+  if (n <= 0) return 0;
+  if (step <= 0) return MMDFN_EINVAL;
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2 = sqrtf(1.0f - powf(beta2, (float)step));
+  adam_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2,
+                                                                      eps, weight_decay, bc1, bc2, grad_scale);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,411 @@
+"""Drop-in nn.Modules for MM-DFN's hot path, running on the sm_100a kernels of libmmdfn_b200.so.
+
+Constructor / forward signatures and state_dict keys mirror the reference (cited per class;
+paths relative to the reference root) so that code/run_train_erc.py works unchanged with
+mm-dfn_b200/dropin first on sys.path.  Sub-modules are created in the reference's order with
+the same nn primitives, hence the same seed yields the same initial weights.
+
+Supported configuration (anything else raises NotImplementedError -- there is no fallback):
+base_model='LSTM', multi_modal=True, modals='avl', graph_type='GDF',
+att_type='concat_subsequently', av_using_lstm=False, with or without use_crn_speaker /
+reason_flag / use_residue=True."""
+import math
+
+import torch
+import torch.nn as nn
+from torch.nn.parameter import Parameter
+
+from . import ops
+from .ops import DialogGeom
+
+
+class BlockAdj:
+    """Opaque handle of the block-compact normalised adjacency (what `create_big_adj` returns
+    instead of the reference's dense (3N,3N) tensor).  `to_dense()` materialises the dense form."""
+
+    def __init__(self, blk, diag, geom):
+        self.blk, self.diag, self.geom = blk, diag, geom
+
+    def to_dense(self):
+        return ops.adj_densify(self.blk.detach(), self.diag.detach(), self.geom)
+
+    @property
+    def shape(self):
+        return (3 * self.geom.N, 3 * self.geom.N)
+
+
+def _geom_of(lengths, device, cache={}):
+    key = (tuple(int(x) for x in lengths), str(device))
+    g = cache.get(key)
+    if g is None:
+        if len(cache) > 64:
+            cache.clear()
+        g = cache[key] = DialogGeom(lengths, device)
+    return g
+
+
+# ------------------------------------------------------------------------------------------------
+# code/model_GCN.py:157-189 (identical copy at code/model_mm.py:10-41)
+# ------------------------------------------------------------------------------------------------
+class GraphConvolution(nn.Module):
+    def __init__(self, in_features, out_features, residual=False, variant=False):
+        super().__init__()
+        self.variant = variant
+        self.in_features = 2 * in_features if variant else in_features
+        self.out_features = out_features
+        self.residual = residual
+        self.weight = Parameter(torch.FloatTensor(self.in_features, self.out_features))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        bound = 1.0 / math.sqrt(self.out_features)
+        self.weight.data.uniform_(-bound, bound)
+
+    def forward(self, input, adj, h0, lamda, alpha, l):
+        """Stand-alone layer (the model itself runs the fused GCNStackFn).  `adj` is a BlockAdj
+        (message aggregate kernel) or a dense tensor (dense GEMM kernel); the two dense
+        contractions run on mmdfn_gemm, the scalar mixes are elementwise glue."""
+        theta = math.log(lamda / l + 1)
+        if isinstance(adj, BlockAdj):
+            hi = ops.SpmmFn.apply(adj.blk, adj.diag, input, adj.geom)
+        else:
+            hi = ops.LinearFn.apply(adj, input.t().contiguous(), None)          # adj @ input
+        if self.variant:
+            g = hi.shape[1]
+            mm = ops.LinearFn.apply(hi, self.weight[:g].t().contiguous(), None) + \
+                ops.LinearFn.apply(h0, self.weight[g:].t().contiguous(), None)
+            r = (1 - alpha) * hi + alpha * h0
+        else:
+            r = (1 - alpha) * hi + alpha * h0
+            mm = ops.LinearFn.apply(r, self.weight.t().contiguous(), None)
+        out = theta * mm + (1 - theta) * r
+        if self.residual:
+            out = out + input
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# code/model_GCN.py:412-488
+# ------------------------------------------------------------------------------------------------
+class GCNII_lyc(nn.Module):
+    def __init__(self, nfeat, nlayers, nhidden, nclass, dropout, lamda, alpha, variant, return_feature, use_residue,
+                 new_graph=False, reason_flag=False):
+        super().__init__()
+        if (nfeat, nhidden) != (200, 100) or not variant:
+            raise NotImplementedError("kernels are specialised for nfeat=200, nhidden=100, variant=True")
+        self.return_feature = return_feature
+        self.use_residue = use_residue
+        self.new_graph = new_graph
+        self.convs = nn.ModuleList([GraphConvolution(nhidden, nhidden, variant=variant) for _ in range(nlayers)])
+        self.fcs = nn.ModuleList([nn.Linear(nfeat, nhidden)])
+        if not return_feature:
+            self.fcs.append(nn.Linear(nfeat + nhidden, nclass))
+        self.act_fn = nn.ReLU()
+        self.dropout = dropout
+        self.alpha = alpha
+        self.lamda = lamda
+        self.rnn_layer = 1
+        self.rnn = nn.LSTM(nhidden, nhidden, self.rnn_layer)
+        self.reason_flag = reason_flag
+
+    def forward(self, x, dia_len, topicLabel, adj=None, test_label=False, masks=None):
+        """x (3N,200), adj: BlockAdj -> (3N,300) = [dropout(x) | z_K].  `masks` (tests only) injects
+        keep-masks {'x','h0','layers'} (uint8) instead of drawing them."""
+        if not isinstance(adj, BlockAdj):
+            raise NotImplementedError("GCNII_lyc needs the block-compact adjacency from MM_GCN.create_big_adj")
+        if not (self.return_feature and self.use_residue):
+            raise NotImplementedError("only return_feature=True, use_residue=True (the GDF configuration)")
+        geom = adj.geom
+        K = len(self.convs)
+        n3 = 3 * geom.N
+        p = float(self.dropout)
+        mx = mh = ml = None
+        scale = 1.0
+        if masks is not None:
+            mx, mh, ml = masks.get("x"), masks.get("h0"), masks.get("layers")
+            scale = 1.0 / (1.0 - p)
+        elif self.training and p > 0:
+            dev = x.device
+            mx, mh = ops.make_mask((n3, 200), p, dev), ops.make_mask((n3, 100), p, dev)
+            ml = ops.make_mask((K, n3, 100), p, dev) if K > 0 else None
+            scale = 1.0 / (1.0 - p)
+        return ops.GCNStackFn.apply(x, adj.blk, adj.diag, geom, K, self.reason_flag, self.lamda, self.alpha, mx, mh, ml,
+                                    scale, self.fcs[0].weight, self.fcs[0].bias, self.rnn.weight_ih_l0,
+                                    self.rnn.weight_hh_l0, self.rnn.bias_ih_l0, self.rnn.bias_hh_l0,
+                                    *[c.weight for c in self.convs])
+
+
+# ------------------------------------------------------------------------------------------------
+# code/model_mm.py:44-180
+# ------------------------------------------------------------------------------------------------
+class MM_GCN(nn.Module):
+    def __init__(self, a_dim, v_dim, l_dim, n_dim, nlayers, nhidden, nclass, dropout, lamda, alpha, variant,
+                 return_feature, use_residue, new_graph='full', n_speakers=2, modals=None, use_speaker=True,
+                 use_modal=False, reason_flag=False, modal_weight=1.0):
+        super().__init__()
+        self.return_feature = return_feature
+        self.use_residue = use_residue
+        self.new_graph = new_graph
+        self.graph_net = GCNII_lyc(nfeat=n_dim, nlayers=nlayers, nhidden=nhidden, nclass=nclass, dropout=dropout,
+                                   lamda=lamda, alpha=alpha, variant=variant, return_feature=return_feature,
+                                   use_residue=use_residue, reason_flag=reason_flag)
+        self.a_fc = nn.Linear(a_dim, n_dim)
+        self.v_fc = nn.Linear(v_dim, n_dim)
+        self.l_fc = nn.Linear(l_dim, n_dim)
+        self.feature_fc = nn.Linear(n_dim * 3 + nhidden * 3, nhidden) if use_residue else nn.Linear(nhidden * 3, nhidden)
+        self.final_fc = nn.Linear(nhidden, nclass)
+        self.act_fn = nn.ReLU()
+        self.dropout = dropout
+        self.alpha = alpha
+        self.lamda = lamda
+        self.modals = modals
+        self.modal_embeddings = nn.Embedding(3, n_dim)
+        self.speaker_embeddings = nn.Embedding(n_speakers, n_dim)
+        self.a_spk_embs = nn.Embedding(n_speakers, n_dim)
+        self.v_spk_embs = nn.Embedding(n_speakers, n_dim)
+        self.l_spk_embs = nn.Embedding(n_speakers, n_dim)
+        self.use_speaker = use_speaker
+        self.use_modal = use_modal
+        self.modal_weight = modal_weight
+
+    def create_big_adj(self, a, v, l, dia_len, modals, modal_weight=1.0):
+        """Block-compact D^-1/2 S D^-1/2 (BlockAdj); differentiable w.r.t. a, v, l."""
+        if len(modals) != 3:
+            raise NotImplementedError("only modals='avl'")
+        X = torch.cat([a, v, l], dim=0)
+        return self.adj_of_stacked(X, _geom_of(dia_len, X.device), modal_weight)
+
+    def adj_of_stacked(self, X, geom, modal_weight=None):
+        blk, diag = ops.AdjFn.apply(X, geom, self.modal_weight if modal_weight is None else modal_weight)
+        return BlockAdj(blk, diag, geom)
+
+    def forward_stacked(self, X, geom, masks=None):
+        """X (3N,200) stacked [a; v; l] -> F (3N,300)."""
+        adj = self.adj_of_stacked(X, geom)
+        return self.graph_net(X, None, None, adj, False, masks)
+
+    def forward(self, a, v, l, dia_len, qmask, test_label=False):
+        if self.modals is None or len(self.modals) != 3:
+            raise NotImplementedError("only modals='avl'")
+        if self.use_speaker or self.use_modal:
+            raise NotImplementedError("use_speaker / use_modal embeddings are off on the MM-DFN path (scripts never set them)")
+        X = torch.cat([a, v, l], dim=0)
+        F_ = self.forward_stacked(X, _geom_of(dia_len, X.device))
+        n = a.shape[0]
+        out = torch.cat([F_[:n], F_[n:2 * n], F_[2 * n:3 * n]], dim=-1)
+        if not self.return_feature:
+            raise NotImplementedError("return_feature=False")
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers for modules the GDF path constructs but never calls (state_dict parity;
+# code/model.py:14-165, 420-437, 718-744).  forward() of the relation-path pieces lives in relation.py.
+# ------------------------------------------------------------------------------------------------
+class SimpleAttention(nn.Module):
+    def __init__(self, input_dim):
+        super().__init__()
+        self.input_dim = input_dim
+        self.scalar = nn.Linear(input_dim, 1, bias=False)
+
+
+class MatchingAttention(nn.Module):
+    def __init__(self, mem_dim, cand_dim, alpha_dim=None, att_type='general'):
+        super().__init__()
+        self.mem_dim, self.cand_dim, self.att_type = mem_dim, cand_dim, att_type
+        if att_type == 'general':
+            self.transform = nn.Linear(cand_dim, mem_dim, bias=False)
+        if att_type == 'general2':
+            self.transform = nn.Linear(cand_dim, mem_dim, bias=True)
+        elif att_type == 'concat':
+            self.transform = nn.Linear(cand_dim + mem_dim, alpha_dim, bias=False)
+            self.vector_prod = nn.Linear(alpha_dim, 1, bias=False)
+
+
+class Attention(nn.Module):
+    def __init__(self, embed_dim, hidden_dim=None, out_dim=None, n_head=1, score_function='dot_product', dropout=0):
+        super().__init__()
+        hidden_dim = embed_dim // n_head if hidden_dim is None else hidden_dim
+        out_dim = embed_dim if out_dim is None else out_dim
+        self.embed_dim, self.hidden_dim, self.n_head, self.score_function = embed_dim, hidden_dim, n_head, score_function
+        self.w_k = nn.Linear(embed_dim, n_head * hidden_dim)
+        self.w_q = nn.Linear(embed_dim, n_head * hidden_dim)
+        self.proj = nn.Linear(n_head * hidden_dim, out_dim)
+        self.dropout = nn.Dropout(dropout)
+        if score_function == 'mlp':
+            self.weight = nn.Parameter(torch.Tensor(hidden_dim * 2))
+        elif score_function == 'bi_linear':
+            self.weight = nn.Parameter(torch.Tensor(hidden_dim, hidden_dim))
+        else:
+            self.register_parameter('weight', None)
+        if self.weight is not None:
+            bound = 1.0 / math.sqrt(hidden_dim)
+            self.weight.data.uniform_(-bound, bound)
+
+
+class MaskedEdgeAttention(nn.Module):
+    """code/model.py:420-471.  forward ('attn1') is provided by relation.py."""
+
+    def __init__(self, input_dim, max_seq_len, no_cuda):
+        super().__init__()
+        self.input_dim = input_dim
+        self.max_seq_len = max_seq_len
+        self.scalar = nn.Linear(input_dim, max_seq_len, bias=False)
+        self.matchatt = MatchingAttention(input_dim, input_dim, att_type='general2')
+        self.simpleatt = SimpleAttention(input_dim)
+        self.att = Attention(input_dim, score_function='mlp')
+        self.no_cuda = no_cuda
+
+    def forward(self, M, lengths, edge_ind):
+        from .relation import masked_edge_attention
+        return masked_edge_attention(self, M, lengths, edge_ind)
+
+
+class MMGatedAttention(nn.Module):
+    """code/model.py:718-781 (constructed by DialogueGNNModel, unused on the GDF path)."""
+
+    def __init__(self, mem_dim, cand_dim, att_type='general'):
+        super().__init__()
+        self.mem_dim, self.cand_dim, self.att_type = mem_dim, cand_dim, att_type
+        self.dropouta, self.dropoutv, self.dropoutl = nn.Dropout(0.5), nn.Dropout(0.5), nn.Dropout(0.5)
+        if att_type == 'av_bg_fusion':
+            self.transform_al = nn.Linear(mem_dim * 2, cand_dim, bias=True)
+            self.scalar_al = nn.Linear(mem_dim, cand_dim)
+            self.transform_vl = nn.Linear(mem_dim * 2, cand_dim, bias=True)
+            self.scalar_vl = nn.Linear(mem_dim, cand_dim)
+        elif att_type == 'general':
+            self.transform_l = nn.Linear(mem_dim, cand_dim, bias=True)
+            self.transform_v = nn.Linear(mem_dim, cand_dim, bias=True)
+            self.transform_a = nn.Linear(mem_dim, cand_dim, bias=True)
+            self.transform_av = nn.Linear(mem_dim * 3, 1)
+            self.transform_al = nn.Linear(mem_dim * 3, 1)
+            self.transform_vl = nn.Linear(mem_dim * 3, 1)
+
+    def forward(self, a, v, l, modals=None):
+        raise NotImplementedError("att_type='gated' is an ablation outside the MM-DFN hot path (SURVEY 8f rank 4)")
+
+
+def simple_batch_graphify(features, lengths, no_cuda):
+    """code/model.py:553-565: (T,B,D) -> (N,D) ragged pack; no edges on the GDF path."""
+    node_features = torch.cat([features[:lengths[j], j, :] for j in range(features.size(1))], dim=0)
+    return node_features, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# code/model.py:784-1407
+# ------------------------------------------------------------------------------------------------
+class DialogueGNNModel(nn.Module):
+    def __init__(self, base_model, D_m, D_g, D_p, D_e, D_h, D_a, graph_hidden_size, n_speakers, max_seq_len,
+                 window_past, window_future, n_classes=7, listener_state=False, context_attention='simple',
+                 dropout_rec=0.5, dropout=0.5, nodal_attention=True, avec=False, no_cuda=False, graph_type='relation',
+                 use_topic=False, alpha=0.1, lamda=0.5, multiheads=6, graph_construct='direct', use_GCN=False,
+                 use_residue=True, dynamic_edge_w=False, D_m_v=512, D_m_a=100, modals='avl', att_type='gated',
+                 av_using_lstm=False, Deep_GCN_nlayers=64, dataset='IEMOCAP', use_speaker=True, use_modal=False,
+                 reason_flag=False, multi_modal=True, use_crn_speaker=False, speaker_weights='1-1-1', modal_weight=1.0):
+        super().__init__()
+        if base_model != 'LSTM' or not multi_modal or sorted(modals) != ['a', 'l', 'v'] or graph_type != 'GDF' \
+                or att_type != 'concat_subsequently' or av_using_lstm or D_e != 100 or graph_hidden_size != 100 \
+                or not use_residue:
+            raise NotImplementedError(
+                "mmdfn_b200 implements the MM-DFN hot path only: base_model='LSTM', multi_modal, modals='avl', "
+                "graph_type='GDF', att_type='concat_subsequently', D_e=graph_hidden_size=100, use_residue")
+        self.base_model, self.avec, self.no_cuda, self.graph_type = base_model, avec, no_cuda, graph_type
+        self.alpha, self.lamda, self.multiheads, self.graph_construct = alpha, lamda, multiheads, graph_construct
+        self.use_topic, self.dropout, self.use_GCN, self.use_residue = use_topic, dropout, use_GCN, use_residue
+        self.dynamic_edge_w = dynamic_edge_w
+        self.return_feature = True
+        self.modals = [x for x in modals]
+        self.use_speaker, self.use_modal = use_speaker, use_modal
+        self.att_type, self.reason_flag, self.multi_modal = att_type, reason_flag, multi_modal
+        self.n_speakers, self.use_crn_speaker = n_speakers, use_crn_speaker
+        self.speaker_weights = list(map(float, speaker_weights.split('-')))
+        self.modal_weight = modal_weight
+        self.av_using_lstm = av_using_lstm
+        self.use_bert_seq = False
+        self.dataset = dataset
+        self.window_past, self.window_future = window_past, window_future
+        self.nodal_attention = nodal_attention
+
+        self.linear_a = nn.Linear(D_m_a, 200)
+        self.linear_v = nn.Linear(D_m_v, 200)
+        self.linear_l = nn.Linear(D_m, 200)
+        self.lstm_l = nn.GRU(input_size=200, hidden_size=D_e, num_layers=2, bidirectional=True, dropout=dropout)
+        self.rnn_parties = nn.GRU(input_size=200, hidden_size=D_e, num_layers=2, bidirectional=True, dropout=dropout)
+        self.att_model = MaskedEdgeAttention(2 * D_e, max_seq_len, self.no_cuda)
+        self.graph_model = MM_GCN(a_dim=2 * D_e, v_dim=2 * D_e, l_dim=2 * D_e, n_dim=2 * D_e, nlayers=Deep_GCN_nlayers,
+                                  nhidden=graph_hidden_size, nclass=n_classes, dropout=self.dropout, lamda=self.lamda,
+                                  alpha=self.alpha, variant=True, return_feature=self.return_feature,
+                                  use_residue=self.use_residue, n_speakers=n_speakers, modals=self.modals,
+                                  use_speaker=self.use_speaker, use_modal=self.use_modal, reason_flag=self.reason_flag,
+                                  modal_weight=self.modal_weight)
+        print("construct " + self.graph_type)
+        self.edge_type_mapping = {}
+        for j in range(n_speakers):
+            for k in range(n_speakers):
+                self.edge_type_mapping[str(j) + str(k) + '0'] = len(self.edge_type_mapping)
+                self.edge_type_mapping[str(j) + str(k) + '1'] = len(self.edge_type_mapping)
+        self.gatedatt = MMGatedAttention(2 * D_e + graph_hidden_size, graph_hidden_size, att_type='general')
+        self.dropout_ = nn.Dropout(self.dropout)
+        self.smax_fc = nn.Linear(300 * len(self.modals), n_classes)
+
+    def _gru_weights(self, gru):
+        return [getattr(gru, k) for k in ops.GRU_KEYS]
+
+    def forward(self, U, qmask, umask, seq_lengths, U_a=None, U_v=None, test_label=False, masks=None):
+        """U = text (T,B,D_m), U_a = audio, U_v = visual, qmask (T,B,S) -> (log_prob (N,C), None x4).
+        `masks` (tests only): injected uint8 keep-masks {'gru_l','gru_p','gcn':{...},'head'}."""
+        if self.use_speaker or self.use_modal:
+            raise NotImplementedError("use_speaker / use_modal are off on the MM-DFN path")
+        if not U.is_cuda:
+            raise ops.MMDFNError("DialogueGNNModel.forward needs CUDA tensors: the B200 path has no CPU fallback")
+        T, B = U.shape[0], U.shape[1]
+        S = qmask.shape[2]
+        dev = U.device
+        geom = _geom_of(seq_lengths, dev)
+        p = float(self.dropout)
+        train_drop = self.training and p > 0 and masks is None
+        scale = 1.0 / (1.0 - p) if (train_drop or masks is not None) else 1.0
+        mk = masks or {}
+        m_l = ops.make_mask((T, B, 200), p, dev) if train_drop else mk.get("gru_l")
+        # k1: the three projections into one stacked table (a, v, l)
+        Utab = ops.Proj3Fn.apply(U_a, U_v, U, self.linear_a.weight, self.linear_a.bias, self.linear_v.weight,
+                                 self.linear_v.bias, self.linear_l.weight, self.linear_l.bias)
+        # k2: text BiGRU over the padded sequence
+        E_l = ops.BiGRU2Fn.apply(Utab[2].reshape(T * B, 200), None, T, B, m_l, scale, *self._gru_weights(self.lstm_l))
+        Q = sel = pos = None
+        if self.use_crn_speaker:
+            # k3: shared speaker-party BiGRU over all (modality, dialogue, speaker) sequences at once
+            pos, _cnt, sel, rowmap = ops.spk_partition(qmask)
+            nseq = 3 * B * S
+            m_p = ops.make_mask((T, nseq, 200), p, dev) if train_drop else mk.get("gru_p")
+            Q = ops.BiGRU2Fn.apply(Utab.reshape(3 * T * B, 200), rowmap, T, nseq, m_p, scale,
+                                   *self._gru_weights(self.rnn_parties))
+        # k3/k4: scatter + speaker-weight combine + ragged pack, written as the stacked graph input
+        X = ops.PartyPackFn.apply(Utab, E_l, Q, geom, sel, pos, S, tuple(self.speaker_weights))
+        gm = mk.get("gcn") if masks is not None else None
+        F_ = self.graph_model.forward_stacked(X, geom, gm)
+        m_h = ops.make_mask((geom.N, 900), p, dev) if train_drop else mk.get("head")
+        log_prob = ops.HeadFn.apply(F_, geom.N, m_h, scale, self.smax_fc.weight, self.smax_fc.bias)
+        return log_prob, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# code/loss.py:5-34
+# ------------------------------------------------------------------------------------------------
+class FocalLoss(nn.Module):
+    def __init__(self, gamma=0, alpha=None, size_average=True):
+        super().__init__()
+        self.gamma = gamma
+        self.alpha = alpha
+        if isinstance(alpha, (float, int)):
+            self.alpha = torch.Tensor([alpha, 1 - alpha])
+        if isinstance(alpha, list):
+            self.alpha = torch.Tensor(alpha)
+        self.size_average = size_average
+
+    def forward(self, input, target):
+        if input.dim() > 2:
+            input = input.view(input.size(0), input.size(1), -1).transpose(1, 2).contiguous().view(-1, input.size(1))
+        if self.alpha is not None and (self.alpha.device != input.device or self.alpha.dtype != input.dtype):
+            self.alpha = self.alpha.to(device=input.device, dtype=input.dtype)
+        return ops.FocalLossFn.apply(input, target, self.alpha, self.gamma, self.size_average)

@@ -1,0 +1,418 @@
+"""torch.autograd bindings of the C ABI (include/mmdfn_b200.h).
+
+PyTorch is used for device memory, streams and the autograd tape only; every arithmetic
+step of the hot path is a kernel of libmmdfn_b200.so.  Nothing here falls back to torch
+ops or to the CPU."""
+import ctypes
+import itertools
+
+import torch
+
+from ._lib import MMDFNError, call, ptr, ptr_table, query, stream
+
+F32 = torch.float32
+U8 = torch.uint8
+
+
+def _empty(shape, device, dtype=F32):
+    return torch.empty(shape, device=device, dtype=dtype)
+
+
+def _f32c(t):
+    """contiguous fp32 CUDA view of t (no copy when already so)."""
+    if not t.is_cuda:
+        raise MMDFNError("mmdfn_b200 needs CUDA tensors: the hot path has no CPU fallback")
+    if t.dtype != F32:
+        t = t.float()
+    return t.contiguous()
+
+
+class DialogGeom:
+    """Ragged geometry of one batch: dialogue i owns rows dia_off[i]..dia_off[i+1]-1 of each
+    modality third of every (3N, .) array and 3*L_i^2 floats of the block-compact adjacency."""
+
+    def __init__(self, lengths, device):
+        self.lengths = [int(x) for x in lengths]
+        self.B = len(self.lengths)
+        self.N = int(sum(self.lengths))
+        self.Lmax = int(max(self.lengths)) if self.lengths else 0
+        off = [0] + list(itertools.accumulate(self.lengths))
+        blk = [0] + list(itertools.accumulate(3 * L * L for L in self.lengths))
+        self.nblk = blk[-1]
+        self.device = device
+        self.dia_off = torch.tensor(off, dtype=torch.int32).to(device)
+        self.blk_off = torch.tensor(blk, dtype=torch.int64).to(device)
+
+    def args(self):
+        return (self.B, self.N, self.Lmax, ptr(self.dia_off, torch.int32), ptr(self.blk_off, torch.int64))
+
+
+# ---------------------------------------------------------------------------------------------
+# dropout keep-masks (counter based; one launch per mask)
+# ---------------------------------------------------------------------------------------------
+_mask_counter = [0]
+
+
+def make_mask(shape, p, device):
+    n = 1
+    for s in shape:
+        n *= int(s)
+    m = _empty(shape, device, U8)
+    seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    call("mmdfn_dropout_mask", n, float(p), seed, _mask_counter[0], ptr(m, U8), stream())
+    _mask_counter[0] = (_mask_counter[0] + n) & 0xFFFFFFFFFFFFFFFF
+    return m
+
+
+# ---------------------------------------------------------------------------------------------
+# k1: projections
+# ---------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b over the last dim (nn.Linear)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x2 = _f32c(x).reshape(-1, x.shape[-1])
+        w = _f32c(w)
+        rows, K = x2.shape
+        n_out = w.shape[0]
+        y = _empty((rows, n_out), x.device)
+        call("mmdfn_gemm", 0, 1, rows, n_out, K, 1.0, ptr(x2), K, ptr(w), K, 0.0, ptr(y), n_out,
+             ptr(_f32c(b)) if b is not None else None, 0, stream())
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = b is not None
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], n_out)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        rows, K = x2.shape
+        n_out = w.shape[0]
+        dy2 = _f32c(dy).reshape(rows, n_out)
+        dx = dw = db = None
+        st = stream()
+        if ctx.needs_input_grad[0]:
+            dx = _empty((rows, K), dy.device)
+            call("mmdfn_gemm", 0, 0, rows, K, n_out, 1.0, ptr(dy2), n_out, ptr(w), K, 0.0, ptr(dx), K, None, 0, st)
+            dx = dx.view(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            dw = _empty((n_out, K), dy.device)
+            call("mmdfn_gemm", 1, 0, n_out, K, rows, 1.0, ptr(dy2), n_out, ptr(x2), K, 0.0, ptr(dw), K, None, 0, st)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _empty((n_out,), dy.device)
+            call("mmdfn_colsum", rows, n_out, ptr(dy2), n_out, 0.0, ptr(db), st)
+        return dx, dw, db
+
+
+class Proj3Fn(torch.autograd.Function):
+    """U (3,T,B,200) = stack over (a, v, l) of x_m W_m^T + b_m   (code/model.py:1065,1094,1129)."""
+
+    @staticmethod
+    def forward(ctx, xa, xv, xl, wa, ba, wv, bv, wl, bl):
+        xs = [_f32c(x) for x in (xa, xv, xl)]
+        ws = [_f32c(w) for w in (wa, wv, wl)]
+        bs = [_f32c(b) for b in (ba, bv, bl)]
+        T, B = xs[0].shape[0], xs[0].shape[1]
+        rows = T * B
+        U = _empty((3, T, B, 200), xa.device)
+        st = stream()
+        for m in range(3):
+            K = xs[m].shape[2]
+            call("mmdfn_gemm", 0, 1, rows, 200, K, 1.0, ptr(xs[m]), K, ptr(ws[m]), K, 0.0,
+                 U.data_ptr() + m * rows * 200 * 4, 200, ptr(bs[m]), 0, st)
+        ctx.save_for_backward(*xs, *ws)
+        return U
+
+    @staticmethod
+    def backward(ctx, dU):
+        xs, ws = ctx.saved_tensors[:3], ctx.saved_tensors[3:]
+        dU = _f32c(dU)
+        T, B = xs[0].shape[0], xs[0].shape[1]
+        rows = T * B
+        st = stream()
+        out = [None] * 9
+        for m in range(3):
+            K = xs[m].shape[2]
+            g = dU.data_ptr() + m * rows * 200 * 4
+            if ctx.needs_input_grad[m]:
+                dx = _empty(xs[m].shape, dU.device)
+                call("mmdfn_gemm", 0, 0, rows, K, 200, 1.0, g, 200, ptr(ws[m]), K, 0.0, ptr(dx), K, None, 0, st)
+                out[m] = dx
+            dw = _empty((200, K), dU.device)
+            call("mmdfn_gemm", 1, 0, 200, K, rows, 1.0, g, 200, ptr(xs[m]), K, 0.0, ptr(dw), K, None, 0, st)
+            db = _empty((200,), dU.device)
+            call("mmdfn_colsum", rows, 200, g, 200, 0.0, ptr(db), st)
+            out[3 + 2 * m], out[4 + 2 * m] = dw, db
+        return tuple(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# k2: 2-layer bidirectional GRU
+# ---------------------------------------------------------------------------------------------
+GRU_KEYS = [f"{k}_l{l}{sfx}" for l in (0, 1) for sfx in ("", "_reverse")
+            for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+
+
+class BiGRU2Fn(torch.autograd.Function):
+    """x (rows,200) [+ rowmap (T,nseq) gather] -> y (T,nseq,200).  16 weights in GRU_KEYS order."""
+
+    @staticmethod
+    def forward(ctx, x, rowmap, T, nseq, mask, mask_scale, *w):
+        x = _f32c(x)
+        w = [_f32c(t) for t in w]
+        rows = x.shape[0]
+        y = _empty((T, nseq, 200), x.device)
+        ws = _empty((query("mmdfn_bigru2_ws_floats", T, nseq, rows),), x.device)
+        tab = ptr_table(w)
+        call("mmdfn_bigru2_fwd", T, nseq, rows, ptr(x), ptr(rowmap, torch.int32), tab, ptr(mask, U8),
+             float(mask_scale), ptr(y), ptr(ws), stream())
+        ctx.save_for_backward(x, y, ws, *w)
+        ctx.rowmap, ctx.mask, ctx.mask_scale, ctx.T, ctx.nseq = rowmap, mask, float(mask_scale), T, nseq
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, ws = ctx.saved_tensors[:3]
+        w = list(ctx.saved_tensors[3:])
+        T, nseq, rows = ctx.T, ctx.nseq, x.shape[0]
+        dy = _f32c(dy)
+        dx = _empty(x.shape, x.device) if ctx.needs_input_grad[0] else None
+        dw = [_empty(t.shape, x.device) for t in w]
+        wsb = _empty((query("mmdfn_bigru2_bwd_ws_floats", T, nseq, rows),), x.device)
+        tab, dtab = ptr_table(w), ptr_table(dw)
+        call("mmdfn_bigru2_bwd", T, nseq, rows, ptr(x), ptr(ctx.rowmap, torch.int32), tab, ptr(ctx.mask, U8),
+             ctx.mask_scale, ptr(y), ptr(dy), ptr(ws), ptr(dx), 0, dtab, ptr(wsb), stream())
+        return (dx, None, None, None, None, None, *dw)
+
+
+# ---------------------------------------------------------------------------------------------
+# k3/k4: speaker partition (integer) and fused scatter + combine + ragged pack
+# ---------------------------------------------------------------------------------------------
+def spk_partition(qmask, want_rowmap=True):
+    """qmask (T,B,S) -> pos (T,B,S), cnt (B,S), sel (T,B), rowmap (T, 3*B*S) int32."""
+    qmask = _f32c(qmask)
+    T, B, S = qmask.shape
+    dev = qmask.device
+    pos = _empty((T, B, S), dev, torch.int32)
+    cnt = _empty((B, S), dev, torch.int32)
+    sel = _empty((T, B), dev, torch.int32)
+    rowmap = _empty((T, 3 * B * S), dev, torch.int32) if want_rowmap else None
+    call("mmdfn_spk_partition", T, B, S, ptr(qmask), ptr(pos, torch.int32), ptr(cnt, torch.int32),
+         ptr(sel, torch.int32), ptr(rowmap, torch.int32), stream())
+    return pos, cnt, sel, rowmap
+
+
+class PartyPackFn(torch.autograd.Function):
+    """X (3N,200): rows (m, off_b + t) = base_m[t,b] + w_m * Q[pos[t,b,sel], (m*B+b)*S+sel]; bases are
+    U[0], U[1] (raw projections) and E_l (text BiGRU output)."""
+
+    @staticmethod
+    def forward(ctx, U, E_l, Q, geom, sel, pos, S, weights):
+        U, E_l = _f32c(U), _f32c(E_l)
+        Q = _f32c(Q) if Q is not None else None
+        _, T, B, _ = U.shape
+        X = _empty((3 * geom.N, 200), U.device)
+        rows = T * B * 200 * 4
+        call("mmdfn_party_pack_fwd", T, B, S, geom.N, ptr(geom.dia_off, torch.int32), ptr(sel, torch.int32),
+             ptr(pos, torch.int32), U.data_ptr(), U.data_ptr() + rows, ptr(E_l), ptr(Q), float(weights[0]),
+             float(weights[1]), float(weights[2]), ptr(X), stream())
+        ctx.geom, ctx.sel, ctx.pos, ctx.S, ctx.weights = geom, sel, pos, S, weights
+        ctx.shape = (T, B)
+        ctx.q_shape = None if Q is None else tuple(Q.shape)
+        return X
+
+    @staticmethod
+    def backward(ctx, dX):
+        dX = _f32c(dX)
+        T, B = ctx.shape
+        geom = ctx.geom
+        dU = _empty((3, T, B, 200), dX.device)
+        dU[2].zero_()
+        dE = _empty((T, B, 200), dX.device)
+        dQ = _empty(ctx.q_shape, dX.device) if ctx.q_shape is not None else None
+        rows = T * B * 200 * 4
+        call("mmdfn_party_pack_bwd", T, B, ctx.S, geom.N, ptr(geom.dia_off, torch.int32), ptr(ctx.sel, torch.int32),
+             ptr(ctx.pos, torch.int32), ptr(dX), float(ctx.weights[0]), float(ctx.weights[1]), float(ctx.weights[2]),
+             dU.data_ptr(), dU.data_ptr() + rows, ptr(dE), ptr(dQ), stream())
+        return dU, dE, dQ, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------
+# k5: block-compact adjacency
+# ---------------------------------------------------------------------------------------------
+class AdjFn(torch.autograd.Function):
+    """X (3N,200) -> (adj_blk (sum 3L^2), adj_diag (3,N)), differentiable w.r.t. X."""
+
+    @staticmethod
+    def forward(ctx, X, geom, modal_weight):
+        X = _f32c(X)
+        dev = X.device
+        N = geom.N
+        adj_blk = _empty((geom.nblk,), dev)
+        adj_diag = _empty((3, N), dev)
+        dinv, rinv, deg = _empty((3 * N,), dev), _empty((3 * N,), dev), _empty((3 * N,), dev)
+        cos_blk, cos_diag = _empty((geom.nblk,), dev), _empty((3, N), dev)
+        call("mmdfn_adj_fwd", *geom.args(), ptr(X), float(modal_weight), ptr(adj_blk), ptr(adj_diag), ptr(dinv),
+             ptr(rinv), ptr(cos_blk), ptr(cos_diag), ptr(deg), stream())
+        ctx.save_for_backward(X, adj_blk, adj_diag, dinv, rinv, cos_blk, cos_diag)
+        ctx.geom, ctx.modal_weight = geom, float(modal_weight)
+        return adj_blk, adj_diag
+
+    @staticmethod
+    def backward(ctx, d_blk, d_diag):
+        X, adj_blk, adj_diag, dinv, rinv, cos_blk, cos_diag = ctx.saved_tensors
+        geom = ctx.geom
+        dev = X.device
+        d_blk = _f32c(d_blk).clone() if d_blk is not None else torch.zeros_like(adj_blk)   # clobbered below
+        d_diag = _f32c(d_diag) if d_diag is not None else torch.zeros_like(adj_diag)
+        dX = _empty(X.shape, dev)
+        dd = _empty((3 * geom.N,), dev)
+        call("mmdfn_adj_bwd", *geom.args(), ptr(X), ctx.modal_weight, ptr(adj_blk), ptr(adj_diag), ptr(dinv), ptr(rinv),
+             ptr(cos_blk), ptr(cos_diag), ptr(d_blk), ptr(d_diag), None, ptr(dX), ptr(dd), stream())
+        return dX, None, None
+
+
+def adj_densify(adj_blk, adj_diag, geom):
+    dense = _empty((3 * geom.N, 3 * geom.N), adj_blk.device)
+    call("mmdfn_adj_densify", *geom.args(), ptr(adj_blk), ptr(adj_diag), ptr(dense), stream())
+    return dense
+
+
+class SpmmFn(torch.autograd.Function):
+    """y = A_hat x on the block-compact adjacency (torch.spmm(adj, input), code/model_GCN.py:178)."""
+
+    @staticmethod
+    def forward(ctx, adj_blk, adj_diag, x, geom):
+        x = _f32c(x)
+        G = x.shape[1]
+        y = _empty(x.shape, x.device)
+        call("mmdfn_adj_spmm", *geom.args(), ptr(adj_blk), ptr(adj_diag), ptr(x), G, ptr(y), stream())
+        ctx.save_for_backward(adj_blk, adj_diag, x)
+        ctx.geom = geom
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        adj_blk, adj_diag, x = ctx.saved_tensors
+        geom = ctx.geom
+        dy = _f32c(dy)
+        G = x.shape[1]
+        d_blk = d_diag = dx = None
+        if ctx.needs_input_grad[2]:
+            dx = _empty(x.shape, x.device)    # A_hat is symmetric: dx = A_hat dy
+            call("mmdfn_adj_spmm", *geom.args(), ptr(adj_blk), ptr(adj_diag), ptr(dy), G, ptr(dx), stream())
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            d_blk, d_diag = _empty(adj_blk.shape, x.device), _empty(adj_diag.shape, x.device)
+            call("mmdfn_adj_grad", *geom.args(), ptr(dy), ptr(x), G, ptr(d_blk), ptr(d_diag), 0, stream())
+        return d_blk, d_diag, dx, None
+
+
+# ---------------------------------------------------------------------------------------------
+# k6/k7/k8: GCNII_lyc stack
+# ---------------------------------------------------------------------------------------------
+class GCNStackFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, adj_blk, adj_diag, geom, K, reason_flag, lamda, alpha, mask_x, mask_h0, mask_layers,
+                mask_scale, W0, b0, w_ih, w_hh, b_ih, b_hh, *convW):
+        X = _f32c(X)
+        dev = X.device
+        n3 = 3 * geom.N
+        convW = [_f32c(w) for w in convW]
+        W0, b0, w_ih, w_hh, b_ih, b_hh = (_f32c(t) for t in (W0, b0, w_ih, w_hh, b_ih, b_hh))
+        F_ = _empty((n3, 300), dev)
+        ws = _empty((query("mmdfn_gcn_stack_ws_floats", n3, K),), dev)
+        tab = ptr_table(convW) if K > 0 else None
+        call("mmdfn_gcn_stack_fwd", *geom.args(), ptr(adj_blk), ptr(adj_diag), ptr(X), K, int(reason_flag),
+             float(lamda), float(alpha), ptr(W0), ptr(b0), tab, ptr(w_ih), ptr(w_hh), ptr(b_ih), ptr(b_hh),
+             ptr(mask_x, U8), ptr(mask_h0, U8), ptr(mask_layers, U8), float(mask_scale), ptr(F_), ptr(ws), stream())
+        ctx.save_for_backward(adj_blk, adj_diag, F_, ws, W0, w_ih, w_hh, *convW)
+        ctx.cfg = (geom, K, int(reason_flag), float(lamda), float(alpha), mask_x, mask_h0, mask_layers, float(mask_scale))
+        return F_
+
+    @staticmethod
+    def backward(ctx, dF):
+        adj_blk, adj_diag, F_, ws, W0, w_ih, w_hh = ctx.saved_tensors[:7]
+        convW = list(ctx.saved_tensors[7:])
+        geom, K, reason_flag, lamda, alpha, mask_x, mask_h0, mask_layers, mask_scale = ctx.cfg
+        dev = F_.device
+        n3 = 3 * geom.N
+        dF = _f32c(dF)
+        dX = _empty((n3, 200), dev)
+        want_adj = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        d_blk = _empty(adj_blk.shape, dev) if want_adj else None
+        d_diag = _empty(adj_diag.shape, dev) if want_adj else None
+        if want_adj and K == 0:
+            d_blk.zero_(); d_diag.zero_()
+        dW0, db0 = _empty(W0.shape, dev), _empty((100,), dev)
+        dw_ih, dw_hh = _empty((400, 100), dev), _empty((400, 100), dev)
+        db_ih, db_hh = _empty((400,), dev), _empty((400,), dev)
+        if not reason_flag:
+            for t in (dw_ih, dw_hh, db_ih, db_hh):
+                t.zero_()
+        dconv = [_empty((200, 100), dev) for _ in range(K)]
+        wsb = _empty((query("mmdfn_gcn_stack_bwd_ws_floats", n3),), dev)
+        tab = ptr_table(convW) if K > 0 else None
+        dtab = ptr_table(dconv) if K > 0 else None
+        call("mmdfn_gcn_stack_bwd", *geom.args(), ptr(adj_blk), ptr(adj_diag), K, reason_flag, lamda, alpha, ptr(W0),
+             tab, ptr(w_ih), ptr(w_hh), ptr(mask_x, U8), ptr(mask_h0, U8), ptr(mask_layers, U8), mask_scale,
+             ptr(F_), ptr(ws), ptr(dF), ptr(dX), ptr(d_blk), ptr(d_diag), ptr(dW0), ptr(db0), dtab, ptr(dw_ih),
+             ptr(dw_hh), ptr(db_ih), ptr(db_hh), ptr(wsb), stream())
+        return (dX, d_blk, d_diag, None, None, None, None, None, None, None, None, None,
+                dW0, db0, dw_ih, dw_hh, db_ih, db_hh, *dconv)
+
+
+# ---------------------------------------------------------------------------------------------
+# k9: head and focal loss
+# ---------------------------------------------------------------------------------------------
+class HeadFn(torch.autograd.Function):
+    """log_softmax(relu(dropout([F_a | F_v | F_l])) Wc^T + bc)  (code/model.py:1328-1337)."""
+
+    @staticmethod
+    def forward(ctx, F_, N, mask, mask_scale, Wc, bc):
+        F_, Wc, bc = _f32c(F_), _f32c(Wc), _f32c(bc)
+        C = Wc.shape[0]
+        R = _empty(F_.shape, F_.device)
+        lp = _empty((N, C), F_.device)
+        call("mmdfn_head_fwd", N, C, ptr(F_), ptr(mask, U8), float(mask_scale), ptr(Wc), ptr(bc), ptr(R), ptr(lp), stream())
+        ctx.save_for_backward(R, lp, Wc)
+        ctx.mask, ctx.mask_scale, ctx.N = mask, float(mask_scale), N
+        return lp
+
+    @staticmethod
+    def backward(ctx, dlp):
+        R, lp, Wc = ctx.saved_tensors
+        N, C = ctx.N, Wc.shape[0]
+        dev = R.device
+        dlp = _f32c(dlp)
+        dF, dWc, dbc = _empty(R.shape, dev), _empty(Wc.shape, dev), _empty((C,), dev)
+        scratch = _empty((max(N, 1), C), dev)
+        call("mmdfn_head_bwd", N, C, ptr(ctx.mask, U8), ctx.mask_scale, ptr(Wc), ptr(R), ptr(lp), ptr(dlp), ptr(dF),
+             ptr(dWc), ptr(dbc), ptr(scratch), stream())
+        return dF, None, None, None, dWc, dbc
+
+
+class FocalLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, log_prob, target, alpha, gamma, size_average):
+        log_prob = _f32c(log_prob)
+        target = target.contiguous().view(-1)
+        if target.dtype != torch.int64:
+            target = target.long()
+        N, C = log_prob.shape
+        loss = _empty((1,), log_prob.device)
+        call("mmdfn_focal_loss_fwd", N, C, ptr(log_prob), ptr(target, torch.int64), ptr(alpha), float(gamma),
+             int(size_average), ptr(loss), stream())
+        ctx.save_for_backward(log_prob, target, alpha)
+        ctx.gamma, ctx.size_average = float(gamma), int(size_average)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        log_prob, target, alpha = ctx.saved_tensors
+        N, C = log_prob.shape
+        dlp = _empty(log_prob.shape, log_prob.device)
+        dloss = _f32c(dloss).reshape(1)
+        call("mmdfn_focal_loss_bwd", N, C, ptr(log_prob), ptr(target, torch.int64), ptr(alpha), ctx.gamma,
+             ctx.size_average, ptr(dloss), ptr(dlp), stream())
+        return dlp, None, None, None, None
