@@ -33,6 +33,8 @@ extern "C" {
 
 /* Library identification: returns the ABI version (1). */
 int mmdfn_abi_version(void);
+/* Number of kernel launches this library has issued in this process (monotonic; for bench accounting). */
+long long mmdfn_launch_count(void);
 
 /* ---- k1 + every dense contraction --------------------------------------------------------
  * C[M,N] = act(alpha * op(A) op(B) + beta * C + bias[N]); op(A)(m,k) = transA ? A[k*lda+m] : A[m*lda+k];

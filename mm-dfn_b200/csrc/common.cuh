@@ -8,10 +8,14 @@ namespace mmdfn {
 
 typedef long long i64;
 
+// process-wide count of kernel launches issued by this library (bench.py reports it as gpu_launches)
+extern unsigned long long g_launch_count;
+
 #define MMDFN_LAUNCH_CHECK()                              \
   do {                                                    \
     cudaError_t e__ = cudaGetLastError();                 \
     if (e__ != cudaSuccess) return (int)e__;              \
+    ++::mmdfn::g_launch_count;                            \
   } while (0)
 
 #define MMDFN_TRY(expr)                                   \

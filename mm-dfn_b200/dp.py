@@ -1,0 +1,79 @@
+"""Data-parallel training step for the MM-DFN hot path.
+
+One process per GPU.  Dialogues are independent units, so each rank runs the whole
+forward/backward on its shard of the batch (padded to the GLOBAL max length T, which is the
+only cross-dialogue coupling) and the only collective is ONE NCCL all-reduce (sum)
+per step over a single flat fp32 gradient bucket, followed by a fused flat-buffer Adam(+L2)
+kernel (optim.Adam(lr, weight_decay=l2), code/run_train_erc.py:512).
+
+FocalLoss is a mean over the batch's utterances (code/loss.py:34): each rank scales its local
+loss by N_rank / N_global so that the summed gradients equal the single-process gradient even
+when shards hold different numbers of utterances.  Parameters the reference never touches on
+this path (grad is None there; Adam skips them) stay outside the bucket."""
+import torch
+import torch.distributed as dist
+
+from ._lib import call, ptr, stream
+
+# parameters that receive a gradient on the GDF path ("Used on GDF path")
+USED_PREFIXES = ("linear_a.", "linear_v.", "linear_l.", "lstm_l.", "rnn_parties.", "graph_model.graph_net.fcs.0.",
+                 "graph_model.graph_net.convs.", "graph_model.graph_net.rnn.", "smax_fc.")
+
+
+def used_parameters(model):
+    return [(n, p) for n, p in model.named_parameters() if n.startswith(USED_PREFIXES)]
+
+
+def shard_dialogues(n_dialogues, rank, world):
+    """contiguous shard [lo, hi) of the dialogue axis for this rank"""
+    per, rem = divmod(n_dialogues, world)
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)
+
+
+class FlatAdamTrainer:
+    """Flat parameter / gradient buckets + one all-reduce + one fused Adam launch per step."""
+
+    def __init__(self, model, loss_fn, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, process_group=None):
+        self.model, self.loss_fn = model, loss_fn
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        named = used_parameters(model)
+        self.names = [n for n, _ in named]
+        params = [p for _, p in named]
+        dev = params[0].device
+        total = sum(p.numel() for p in params)
+        self.flat_p = torch.empty(total, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
+        off = 0
+        for p in params:
+            n = p.numel()
+            self.flat_p[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + n].view_as(p)          # parameters become views of the bucket
+            p.grad = self.flat_g[off:off + n].view_as(p)          # autograd accumulates in place into the bucket
+            off += n
+        self.total = total
+        self.step_count = 0
+        if self.world > 1:                                        # replicas start identical
+            dist.broadcast(self.flat_p, src=0, group=self.pg)
+
+    def step(self, textf, qmask, umask, lengths, acouf, visuf, label, n_global=None):
+        """One fwd + bwd + (all-reduce) + Adam step on this rank's shard.  Returns the local loss tensor
+        (already scaled by N_rank/N_global; the sum over ranks is the global mean loss)."""
+        self.flat_g.zero_()
+        log_prob = self.model(textf, qmask, umask, lengths, acouf, visuf)[0]
+        loss = self.loss_fn(log_prob, label)
+        n_local = int(sum(lengths))
+        if n_global is not None and n_global != n_local:
+            loss = loss * (float(n_local) / float(n_global))
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+        self.step_count += 1
+        call("mmdfn_adam_step", self.total, ptr(self.flat_p), ptr(self.flat_g), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+             float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd),
+             self.step_count, 1.0, stream())
+        return loss.detach()
