@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- utterances/sec (fwd+bwd+Adam) of the MM-DFN hot path on synthetic IEMOCAP-shaped batches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]/[3], SURVEY.md 8d "C4"): per GPU 32 dialogues x 100 utterances,
+text/audio/visual features 100/512/1024-d, 2 speakers, 6 classes, 2 GCN layers + LSTM fusion gate
+(`--reason_flag`), speaker-party encoders on, dropout 0.4 (train mode).  Weak scaling: the per-GPU
+shard is fixed, the global batch is 32*N dialogues; the only collective is one NCCL all-reduce of a
+flat gradient bucket per step.
+
+One JSON line on rank 0.  `value` = whole-job utterances/s with inputs resident in HBM; `e2e` = the
+same step through the public API with pinned-host inputs copied H2D and the loss read back D2H every
+step; `roofline` = the graph-conv message-aggregate kernel (k6) timed alone with CUDA events against
+the measured HBM peak; `cpu_baseline` = the oracle's faithful port of the reference algorithm timed on
+the host cores on a bounded sample.  `--impl reference` times that CPU port only."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+DIALOGUES_PER_GPU = 32
+UTT = 100
+D_T, D_A, D_V = 100, 512, 1024
+SPEAKERS, CLASSES, LAYERS = 2, 6, 2
+SPK_W = "3-0-1"
+DROPOUT = 0.4
+LR, L2 = 1e-4, 1e-4
+GAMMA = 1.0
+N_BATCHES = 8                      # distinct input batches rotated so that step inputs exceed L2
+CPU_SAMPLE_DIALOGUES = 8
+METRIC = "utterances/sec (fwd+bwd) IEMOCAP-shape"
+UNIT = "utterances/s"
+
+
+def workload_config(n_gpus):
+    per_gpu_bytes = UTT * DIALOGUES_PER_GPU * (D_T + D_A + D_V + SPEAKERS) * 4
+    return {"workload": "BASELINE configs[1]/[3] (SURVEY C4 shape): synthetic IEMOCAP-shape, 32 dialogues x 100 "
+                        "utterances per GPU, 100/512/1024-d T/A/V, S=2, C=6, 2 GCN layers + LSTM fusion gate, "
+                        "crn-speaker encoders, dropout 0.4, FocalLoss(gamma=1), Adam(lr=1e-4, l2=1e-4)",
+            "dialogues_per_gpu": DIALOGUES_PER_GPU, "utterances_per_dialogue": UTT, "global_dialogues": DIALOGUES_PER_GPU * n_gpus,
+            "gcn_layers": LAYERS, "parallelism": f"dp{n_gpus} (dialogue shards, 1 NCCL all-reduce/step)",
+            "l2_policy": f"inputs rotate over {N_BATCHES} distinct batches ({N_BATCHES * per_gpu_bytes / 1e6:.0f} MB > 126 MB L2)"}
+
+
+def make_batches(n, seed0):
+    import mmdfn_oracle as O
+    out = []
+    for i in range(n):
+        t, a, v, q, u, lab = O.synthetic_batch([UTT] * DIALOGUES_PER_GPU, D_T, D_A, D_V, SPEAKERS, CLASSES, seed=seed0 + i)
+        out.append((t, a, v, q, u, lab))
+    return out
+
+
+def class_weights():
+    return torch.tensor([1 / 0.086747, 1 / 0.144406, 1 / 0.227883, 1 / 0.160585, 1 / 0.127711, 1 / 0.252668])
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's faithful restatement of the reference algorithm (dense (3N)^2 adjacency,
+# per-dialogue loops, D.mm(adj).mm(D)), fwd + bwd (+Adam) on all host threads.
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, n_dialogues=CPU_SAMPLE_DIALOGUES, max_seconds=150.0):
+    import mmdfn_oracle as O
+    from helpers import model_shapes
+    torch.set_num_threads(os.cpu_count() or 1)
+    lengths = [UTT] * n_dialogues
+    t, a, v, q, u, lab = O.synthetic_batch(lengths, D_T, D_A, D_V, SPEAKERS, CLASSES, seed=100)
+    P = {k: w.clone().requires_grad_(True) for k, w in O.formula_weights(model_shapes(D_T, D_A, D_V, SPEAKERS, CLASSES, LAYERS)).items()}
+    used = [w for k, w in P.items() if k.startswith(("linear_", "lstm_l.", "rnn_parties.", "graph_model.graph_net.", "smax_fc."))]
+    opt = torch.optim.Adam(used, lr=LR, weight_decay=L2)
+    cw = class_weights()
+    wts = tuple(float(x) for x in SPK_W.split("-"))
+    gen = torch.Generator().manual_seed(0)
+    T, B, N = UTT, n_dialogues, sum(lengths)
+    keep = 1.0 - DROPOUT
+
+    def drop(shape):
+        return (torch.rand(shape, generator=gen) < keep).float() / keep
+
+    def one_step():
+        masks = {"gru_l": drop((T, B, 200)),
+                 "gru_p": {m: [drop((T, B, 200)) for _ in range(SPEAKERS)] for m in "avl"},
+                 "gcn": {"x": drop((3 * N, 200)), "h0": drop((3 * N, 100)), "layer": [drop((3 * N, 100)) for _ in range(LAYERS)]},
+                 "head": drop((N, 900))}
+        opt.zero_grad(set_to_none=True)
+        lp = O.forward_gdf(P, t, q, lengths, a, v, nlayers=LAYERS, speaker_weights=wts, masks=masks, faithful=True)
+        loss = O.focal_loss(lp, lab, GAMMA, cw)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    t_start = time.perf_counter()
+    for _ in range(warmup):
+        one_step()
+        if time.perf_counter() - t_start > max_seconds / 3:
+            break
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one_step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > max_seconds:
+            break
+    sec = float(np.mean(times))
+    return {"utt_per_s": N / sec, "sec_per_step": sec, "steps_timed": len(times), "cores": torch.get_num_threads(),
+            "sample": f"{n_dialogues} of the workload's {DIALOGUES_PER_GPU} dialogues x {UTT} utterances per step "
+                      f"({N} utterances; the reference's dense (3N)^2 adjacency makes its throughput fall with batch size), "
+                      f"fwd+bwd+Adam, dropout {DROPOUT}, mean of {len(times)} steps"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_steps(max(1, args.steps), max(1, min(args.warmup, 2)), max_seconds=170.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["utt_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": r["steps_timed"], "warmup": min(args.warmup, 2), "ms_per_step": r["sec_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus), "gpu_launches": 0,
+            "cpu_baseline": {"value": r["utt_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["utt_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def roofline_graph_conv(dev):
+    """k6 message aggregate hi = A_hat z on the bench shard, timed alone with CUDA events on the launching
+    stream; operands rotate over enough copies to defeat the 126 MB L2."""
+    from mmdfn_b200 import ops
+    from mmdfn_b200._lib import call, ptr, stream
+    lengths = [UTT] * DIALOGUES_PER_GPU
+    geom = ops.DialogGeom(lengths, dev)
+    N, G = geom.N, 100
+    alg_bytes = 4 * (3 * N * G + 3 * N * G + sum(3 * L * L + 3 * L for L in lengths))     # z in, hi out, A_hat blocks + diagonals
+    copies = max(2, int(300e6 // alg_bytes) + 1)
+    g = torch.Generator(device=dev).manual_seed(0)
+    blk = [torch.rand(geom.nblk, device=dev, generator=g) / UTT for _ in range(copies)]
+    dg = [torch.rand(3, N, device=dev, generator=g) / UTT for _ in range(copies)]
+    z = [torch.randn(3 * N, G, device=dev, generator=g) for _ in range(copies)]
+    y = [torch.empty(3 * N, G, device=dev) for _ in range(copies)]
+    st = stream()
+
+    def launch(i):
+        call("mmdfn_adj_spmm", *geom.args(), ptr(blk[i]), ptr(dg[i]), ptr(z[i]), G, ptr(y[i]), st)
+
+    for i in range(copies):
+        launch(i)
+    torch.cuda.synchronize()
+    reps = 3 * copies
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        launch(i % copies)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    peak, how = measured_peak_gbs()
+    achieved = alg_bytes / (us * 1e-6) / 1e9
+    return {"kernel": "adj_spmm_kernel (k6 graph-conv message aggregate hi = A_hat z, fp32)", "bound": "hbm",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us, "peak_source": how,
+            "note": "launch covers one GCN layer of the 32x100 shard; operands rotated over %d copies (> L2)" % copies}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+
+    import mmdfn_b200
+    from mmdfn_b200.dp import FlatAdamTrainer
+    from mmdfn_b200._lib import query
+    import mmdfn_oracle as O
+    from helpers import model_shapes
+
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    model = mmdfn_b200.DialogueGNNModel(
+        "LSTM", D_T, 150, 150, 100, 100, 100, 100, n_speakers=SPEAKERS, max_seq_len=200, window_past=10, window_future=10,
+        n_classes=CLASSES, dropout=DROPOUT, graph_type="GDF", alpha=0.2, lamda=0.5, D_m_v=D_V, D_m_a=D_A, modals="avl",
+        att_type="concat_subsequently", Deep_GCN_nlayers=LAYERS, use_speaker=False, reason_flag=True, use_crn_speaker=True,
+        speaker_weights=SPK_W)
+    model.load_state_dict(O.formula_weights(model_shapes(D_T, D_A, D_V, SPEAKERS, CLASSES, LAYERS)))   # random-init weights
+    model = model.to(dev).train()
+    loss_fn = mmdfn_b200.FocalLoss(gamma=GAMMA, alpha=class_weights().to(dev))
+    trainer = FlatAdamTrainer(model, loss_fn, lr=LR, weight_decay=L2)
+    torch.manual_seed(1234 + rank)
+
+    host = make_batches(N_BATCHES, seed0=1000 * (rank + 1))              # each rank owns different dialogues
+    pinned = [tuple(x.pin_memory() for x in b) for b in host]
+    resident = [tuple(x.to(dev) for x in b) for b in host]
+    lengths = [UTT] * DIALOGUES_PER_GPU
+    n_local = sum(lengths)
+    n_global = n_local * world
+    h2d_bytes = sum(x.numel() * x.element_size() for x in host[0])
+
+    def step_resident(i):
+        t, a, v, q, u, lab = resident[i % N_BATCHES]
+        return trainer.step(t, q, u, lengths, a, v, lab, n_global)
+
+    def step_e2e(i):
+        t, a, v, q, u, lab = (x.to(dev, non_blocking=True) for x in pinned[i % N_BATCHES])
+        loss = trainer.step(t, q, u, lengths, a, v, lab, n_global)
+        return float(loss)                                               # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / 1e3, wall
+
+    for i in range(W):
+        step_resident(i)
+    for i in range(2):
+        step_e2e(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = query("mmdfn_launch_count")
+    sec, wall = timed(step_resident, K)
+    launches = query("mmdfn_launch_count") - launches0
+    sec_e2e, _ = timed(step_e2e, K)
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        value = n_global * K / sec
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": sec / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+                "e2e": {"value": n_global * K / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                        "ms_per_step": sec_e2e / K * 1e3},
+                "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall}
+        try:
+            line["roofline"] = roofline_graph_conv(dev)
+        except Exception as e:  # pragma: no cover
+            line["roofline"] = {"error": repr(e)}
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_steps(steps=3, warmup=1, max_seconds=60.0)
+            line["cpu_baseline"] = {"value": r["utt_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
