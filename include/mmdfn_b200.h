@@ -133,6 +133,26 @@ int mmdfn_focal_loss_fwd(int N, int C, const float* log_prob, const long long* t
 int mmdfn_focal_loss_bwd(int N, int C, const float* log_prob, const long long* target, const float* alpha,
                          float gamma, int size_average, const float* dloss, float* dlog_prob, void* stream);
 
+/* ---- k10/k11 (relation graph type): edges and masked edge attention ----------------------------
+ * edge_perms + batch_graphify (code/model.py:532-550, 568-611) and MaskedEdgeAttention 'attn1' (:449-471).
+ * Canonical edge order: dialogue, source j, target i ascending; edge_off (B+1) int64 = per-dialogue edge
+ * offsets (host-computed from the lengths), E = edge_off[B].  edge_index (2,E) int64 [row 0 = source j,
+ * row 1 = target i, both with the dialogue's node offset], edge_type (E) int64 = 2*(S*spk_j+spk_i)+(j>=i),
+ * row_ptr (N+1) int64: first edge of each source node, node_dia (N) int32: dialogue of each node. */
+int mmdfn_edges_build(int T, int B, int S, int N, int window_past, int window_future, const int* dia_off,
+                      const long long* edge_off, long long E, const float* qmask, long long* edge_index,
+                      long long* edge_type, long long* row_ptr, int* node_dia, void* stream);
+/* s_all (T*B, ncol) = M W_att[:ncol]^T (mmdfn_gemm), ncol >= Lmax.  edge_norm (E) in edge order;
+ * stat (N,2) = {row max, denominator} saved for the backward. */
+int mmdfn_edge_attn_fwd(int T, int B, int Lmax, int ncol, int window_past, int window_future, const int* dia_off,
+                        const long long* row_ptr, const float* s_all, float* edge_norm, float* stat, void* stream);
+int mmdfn_edge_attn_bwd(int T, int B, int Lmax, int ncol, int window_past, int window_future, const int* dia_off,
+                        const long long* row_ptr, const float* s_all, const float* edge_norm, const float* stat,
+                        const float* g_norm, float* ds_all, void* stream);
+/* dense (B, msl, T) <-> compact (E) edge scores: gather = 0 scatters (dense zero-filled first), 1 gathers */
+int mmdfn_edge_scores_dense(long long E, int B, int msl, int T, const long long* edge_index, const int* node_dia,
+                            const int* dia_off, float* edge_norm, float* dense, int gather, void* stream);
+
 /* ---- support: dropout keep masks, fused flat-buffer Adam(+L2) (code/run_train_erc.py:512) ----- */
 int mmdfn_dropout_mask(long long n, float p, unsigned long long seed, unsigned long long offset,
                        unsigned char* mask, void* stream);
