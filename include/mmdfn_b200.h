@@ -43,6 +43,12 @@ long long mmdfn_launch_count(void);
 int mmdfn_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
                const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int act,
                void* stream);
+/* Same contract on the tcgen05 tensor cores (kind::tf32, accumulators in TMEM) with the 3-term TF32 split
+ * (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo): fp32-level accuracy at tensor-core rate.  mmdfn_gemm dispatches here
+ * for large problems; exposed for tests and profiling. */
+int mmdfn_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
+                  const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int act,
+                  void* stream);
 /* out[n] = beta*out[n] + sum_m A[m*lda+n]   (bias gradients) */
 int mmdfn_colsum(int M, int N, const float* A, long long lda, float beta, float* out, void* stream);
 

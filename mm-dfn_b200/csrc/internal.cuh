@@ -8,6 +8,9 @@ namespace mmdfn {
 // C[M,N] = act(alpha * op(A) op(B) + beta * C + bias[N]); row-major; see mmdfn_gemm.
 int gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64 lda, const float* B, i64 ldb,
          float beta, float* C, i64 ldc, const float* bias, int act, cudaStream_t st);
+// same contract on tcgen05 (3xTF32)
+int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64 lda, const float* B, i64 ldb,
+              float beta, float* C, i64 ldc, const float* bias, int act, cudaStream_t st);
 // out[n] = beta*out[n] + sum_m A[m*lda + n]
 int colsum(int M, int N, const float* A, i64 lda, float beta, float* out, cudaStream_t st);
 int fill_zero(void* p, size_t bytes, cudaStream_t st);

@@ -1,0 +1,61 @@
+"""Standalone check of mmdfn_gemm_tc (tcgen05 3xTF32 GEMM) against fp64, printing the error per shape and mode
+next to the FFMA kernel's; also times both.  Usage (GPU box): python tools/umma_check.py"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from mmdfn_b200 import _lib as L
+
+torch.manual_seed(0)
+dev = "cuda"
+
+def run(name, ta, tb, M, N, K, bias=False, act=0, beta=0.0, alpha=1.0):
+    A = torch.randn((K, M) if ta else (M, K), device=dev)
+    B = torch.randn((N, K) if tb else (K, N), device=dev)
+    C0 = torch.randn(M, N, device=dev)
+    bi = torch.randn(N, device=dev) if bias else None
+    opA = A.double().t() if ta else A.double()
+    opB = B.double().t() if tb else B.double()
+    ref = alpha * (opA @ opB) + beta * C0.double() + (bi.double() if bias else 0)
+    if act: ref = torch.relu(ref)
+    out = {}
+    for fn in ("mmdfn_gemm_tc", "mmdfn_gemm"):
+        C = C0.clone()
+        L.call(fn, int(ta), int(tb), M, N, K, alpha, L.ptr(A), A.shape[1], L.ptr(B), B.shape[1], beta, L.ptr(C), N,
+               L.ptr(bi) if bias else None, act, L.stream())
+        torch.cuda.synchronize()
+        out[fn] = float((C.double() - ref).abs().max())
+        # timing
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            L.call(fn, int(ta), int(tb), M, N, K, alpha, L.ptr(A), A.shape[1], L.ptr(B), B.shape[1], 0.0, L.ptr(C), N,
+                   L.ptr(bi) if bias else None, act, L.stream())
+        e1.record(); torch.cuda.synchronize()
+        out[fn + "_us"] = e0.elapsed_time(e1) * 1e3 / 5
+    gf = 2.0 * M * N * K / 1e9
+    print(f"{name:28s} M={M:6d} N={N:4d} K={K:6d} err_tc={out['mmdfn_gemm_tc']:.2e} err_ffma={out['mmdfn_gemm']:.2e} "
+          f"tc={out['mmdfn_gemm_tc_us']:8.1f}us ({gf/out['mmdfn_gemm_tc_us']*1e3:7.1f} TF/s) ffma={out['mmdfn_gemm_us']:8.1f}us "
+          f"({gf/out['mmdfn_gemm_us']*1e3:6.1f} TF/s)", flush=True)
+    return out["mmdfn_gemm_tc"]
+
+print(torch.cuda.get_device_name(0), flush=True)
+run("NT tiny", 0, 1, 128, 112, 32)
+run("NT one tile K=8", 0, 1, 128, 16, 8)
+run("NT ragged", 0, 1, 130, 100, 100, bias=True, act=1, beta=0.5, alpha=0.7)
+run("NT proj text", 0, 1, 3200, 200, 100, bias=True)
+run("NT proj audio", 0, 1, 3200, 200, 512, bias=True)
+run("NT proj visual", 0, 1, 3200, 200, 1024, bias=True)
+run("NT proj iemocap audio", 0, 1, 3520, 200, 1582, bias=True)
+run("NT proj iemocap visual", 0, 1, 3520, 200, 342, bias=True)
+run("NT gru in-gemm", 0, 1, 19200, 300, 200, bias=True)
+run("NT lstm gates", 0, 1, 9600, 400, 100, bias=True)
+run("NT big", 0, 1, 153600, 300, 200, bias=True)
+run("NN dx", 0, 0, 19200, 200, 300)
+run("NN conv W", 0, 0, 9600, 100, 100, beta=1.0)
+run("NN ragged", 0, 0, 77, 45, 19)
+run("TN dW_ih splitK", 1, 0, 300, 200, 19200)
+run("TN dW small", 1, 0, 100, 100, 9600, beta=1.0)
+run("TN dW proj", 1, 0, 200, 1024, 3200)
+run("TN ragged", 1, 0, 77, 45, 190)
+print("done")
