@@ -95,6 +95,10 @@ int gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64
   if (M == 0 || N == 0) return 0;
   if (!A || !B || !C) return MMDFN_ENULL;
   if (ta && tb) return MMDFN_EINVAL;
+  // large contractions run on the tensor cores (tcgen05 kind::tf32, 3-term split: fp32-level accuracy);
+  // small ones stay on the FFMA tile kernel, whose prologue is cheaper than a TMEM allocation
+  if (2.0 * (double)M * (double)N * (double)K >= 2.0e8)
+    return umma_gemm(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act, st);
   GemmArgs p{A, lda, B, ldb, C, ldc, bias, M, N, K, alpha, beta, act, 1};
   const bool big = (i64)ceil_div(M, 128) * ceil_div(N, 64) >= 148;
   const i64 tiles = big ? (i64)ceil_div(M, 128) * ceil_div(N, 64) : (i64)ceil_div(M, 64) * ceil_div(N, 64);
