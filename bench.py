@@ -254,11 +254,13 @@ def main():
 
     W = max(3, args.warmup)
     K = max(1, args.steps)
-    model = mmdfn_b200.DialogueGNNModel(
-        "LSTM", D_T, 150, 150, 100, 100, 100, 100, n_speakers=SPEAKERS, max_seq_len=200, window_past=10, window_future=10,
-        n_classes=CLASSES, dropout=DROPOUT, graph_type="GDF", alpha=0.2, lamda=0.5, D_m_v=D_V, D_m_a=D_A, modals="avl",
-        att_type="concat_subsequently", Deep_GCN_nlayers=LAYERS, use_speaker=False, reason_flag=True, use_crn_speaker=True,
-        speaker_weights=SPK_W)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):          # the constructor prints "construct GDF" like the reference; stdout is for the JSON line only
+        model = mmdfn_b200.DialogueGNNModel(
+            "LSTM", D_T, 150, 150, 100, 100, 100, 100, n_speakers=SPEAKERS, max_seq_len=200, window_past=10, window_future=10,
+            n_classes=CLASSES, dropout=DROPOUT, graph_type="GDF", alpha=0.2, lamda=0.5, D_m_v=D_V, D_m_a=D_A, modals="avl",
+            att_type="concat_subsequently", Deep_GCN_nlayers=LAYERS, use_speaker=False, reason_flag=True, use_crn_speaker=True,
+            speaker_weights=SPK_W)
     model.load_state_dict(O.formula_weights(model_shapes(D_T, D_A, D_V, SPEAKERS, CLASSES, LAYERS)))   # random-init weights
     model = model.to(dev).train()
     loss_fn = mmdfn_b200.FocalLoss(gamma=GAMMA, alpha=class_weights().to(dev))

@@ -49,6 +49,11 @@ int mmdfn_gemm(int transA, int transB, int M, int N, int K, float alpha, const f
 int mmdfn_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
                   const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int act,
                   void* stream);
+/* profiling aid: 128 x int64 device buffer receiving clock64() phase stamps of CTA 0 of the next mmdfn_gemm_tc launches (NULL = off) */
+int mmdfn_gemm_tc_set_debug(long long* device_buf);
+int mmdfn_gemm_tc_set_variant(int v);
+/* debug aid: reads back the shared-memory word the tensor core uses for each operand element (see umma_probe.cu) */
+int mmdfn_umma_probe(float* out, int N, int lbo, int sbo, int mn_major, int probe_a, void* stream);
 /* out[n] = beta*out[n] + sum_m A[m*lda+n]   (bias gradients) */
 int mmdfn_colsum(int M, int N, const float* A, long long lda, float beta, float* out, void* stream);
 

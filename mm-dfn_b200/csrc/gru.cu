@@ -50,17 +50,27 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(GruFwdArgs p) {
   for (int i = tid; i < NB * GH; i += GRU_THREADS) (&hs[0][0])[i] = 0.f;
   __syncthreads();
 
+  // software pipeline: gate rows of step s+1 and row indices of step s+2 are in flight while step s computes
+  auto slot_of = [&](int step, int b) { return (i64)(dir ? (p.T - 1 - step) : step) * p.nseq + s0 + b; };
+  auto row_of = [&](int step, int b) -> i64 {
+    if (step >= p.T || b >= nb) return -2;
+    const i64 slot = slot_of(step, b);
+    return p.rowmap ? (i64)p.rowmap[slot] : slot;
+  };
+  auto gate_of = [&](i64 row) { return row >= 0 ? p.xg[row * 600 + dir * G3 + j] : (row == -1 ? bi : 0.f); };
+  float xv[NB], xn[NB];
+  i64 rown[NB];
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    xv[b] = gate_of(row_of(0, b));
+    rown[b] = row_of(1, b);
+  }
   for (int step = 0; step < p.T; step++) {
     const int t = dir ? (p.T - 1 - step) : step;
-    float xv[NB];
 #pragma unroll
     for (int b = 0; b < NB; b++) {
-      xv[b] = 0.f;
-      if (b < nb) {
-        const i64 slot = (i64)t * p.nseq + s0 + b;
-        const i64 row = p.rowmap ? (i64)p.rowmap[slot] : slot;
-        xv[b] = row >= 0 ? p.xg[row * 600 + dir * G3 + j] : bi;
-      }
+      xn[b] = gate_of(rown[b]);          // consumed at the top of the next step
+      rown[b] = row_of(step + 2, b);
     }
     float acc[NB];
 #pragma unroll
@@ -104,6 +114,8 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(GruFwdArgs p) {
       }
     }
     __syncthreads();
+#pragma unroll
+    for (int b = 0; b < NB; b++) xv[b] = xn[b];
   }
 }
 
@@ -136,16 +148,37 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(GruBwdArgs p) {
   for (int i = tid; i < NB * G3; i += GRU_THREADS) (&dgh[0][0])[i] = 0.f;
   __syncthreads();
 
-  for (int step = 0; step < p.T; step++) {
+  constexpr int ITEMS = (NB * GH + GRU_THREADS - 1) / GRU_THREADS;
+  struct Pre { float r, z, n, hn, hp, dy; };
+  Pre cur[ITEMS], nxt[ITEMS];
+  auto fetch = [&](int step, Pre (&o)[ITEMS]) {
     const int t = dir ? step : (p.T - 1 - step);       // reverse of the forward visiting order
     const int tp = dir ? t + 1 : t - 1;                // slot that produced h_prev
-    for (int idx = tid; idx < nb * GH; idx += GRU_THREADS) {
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      const int idx = tid + it * GRU_THREADS;
+      o[it] = Pre{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (step < p.T && idx < nb * GH) {
+        const int b = idx / GH, u = idx - b * GH;
+        const i64 slot = (i64)t * p.nseq + s0 + b;
+        const float* g = p.gates + (slot * 2 + dir) * 400;
+        o[it].r = g[u]; o[it].z = g[GH + u]; o[it].n = g[2 * GH + u]; o[it].hn = g[3 * GH + u];
+        o[it].hp = (tp >= 0 && tp < p.T) ? p.y[((i64)tp * p.nseq + s0 + b) * 200 + dir * GH + u] : 0.f;
+        o[it].dy = p.dy[slot * 200 + dir * GH + u];
+      }
+    }
+  };
+  fetch(0, cur);
+  for (int step = 0; step < p.T; step++) {
+    const int t = dir ? step : (p.T - 1 - step);
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      const int idx = tid + it * GRU_THREADS;
+      if (idx >= nb * GH) continue;
       const int b = idx / GH, u = idx - b * GH;
       const i64 slot = (i64)t * p.nseq + s0 + b;
-      const float* g = p.gates + (slot * 2 + dir) * 400;
-      const float r = g[u], z = g[GH + u], n = g[2 * GH + u], hn = g[3 * GH + u];
-      const float hp = (tp >= 0 && tp < p.T) ? p.y[((i64)tp * p.nseq + s0 + b) * 200 + dir * GH + u] : 0.f;
-      const float dht = dh[b][u] + part[0][b][u] + part[1][b][u] + part[2][b][u] + p.dy[slot * 200 + dir * GH + u];
+      const float r = cur[it].r, z = cur[it].z, n = cur[it].n, hn = cur[it].hn, hp = cur[it].hp;
+      const float dht = dh[b][u] + part[0][b][u] + part[1][b][u] + part[2][b][u] + cur[it].dy;
       const float dn = dht * (1.0f - z);
       const float dz = dht * (hp - n);
       const float dn_pre = dn * (1.0f - n * n);
@@ -158,6 +191,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(GruBwdArgs p) {
       dgh[b][u] = dr_pre; dgh[b][GH + u] = dz_pre; dgh[b][2 * GH + u] = dhn_;
       dh[b][u] = dht * z;
     }
+    fetch(step + 1, nxt);                              // lands while the mat-vec below runs
     __syncthreads();
     float acc[NB];
 #pragma unroll
@@ -178,6 +212,8 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(GruBwdArgs p) {
       for (int b = 0; b < NB; b++) part[jp][b][u_mv] = acc[b];
     }
     __syncthreads();
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) cur[it] = nxt[it];
   }
 }
 

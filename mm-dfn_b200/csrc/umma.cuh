@@ -74,9 +74,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint
   return d;
 }
 
-// Instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major.
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Instruction descriptor for kind::tf32, fp32 accumulate; a_mn / b_mn = 1 selects the MN-major operand layout
+// (bits 15 / 16), 0 the K-major one.
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread

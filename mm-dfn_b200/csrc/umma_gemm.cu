@@ -18,18 +18,31 @@
 
 namespace mmdfn {
 
-constexpr int UG_THREADS = 128;
+constexpr int UG_THREADS = 256;       // converter / epilogue threads (warps 0-7)
+constexpr int UG_ALL_THREADS = UG_THREADS + 32;   // + warp 8: the MMA issuer
 constexpr int UG_BN = 112;         // output columns per CTA (N = 100 / 200 / 300 / 400 / 600 -> 1 / 2 / 3 / 4 / 6 tiles)
 constexpr int UG_KC = 16;          // K elements per stage (2 k-steps of 8)
-constexpr int UG_STAGES = 3;
+constexpr int UG_STAGES = 2;       // UMMA operand stages (hi/lo split tiles)
+// K-major operand stage (source rows K-contiguous): core matrix = 8 rows x 16 B; the 4 core matrices of a row group
+// (KC = 16) are contiguous, row groups are UG_SBO apart (512 B + 16 B pad so that row groups spread over banks).
 constexpr int UG_LBO = 128;        // bytes between the two core matrices of one k-step
-constexpr int UG_SBO = 528;        // bytes between 8-row groups: 4 core matrices (512 B) + 16 B pad (bank spread)
+constexpr int UG_SBO = 528;        // bytes between 8-row groups
+// MN-contiguous sources are transposed on the way into the same K-major layout (the tf32 MMA returned zeros with the
+// MN-major descriptor bit in the SWIZZLE_NONE layout on this part -- tools/umma_probe.py -- so one layout serves all).
 constexpr int UG_TMEM_COLS = 256;  // [0,112): hi*hi accumulator, [128,240): correction accumulator
 constexpr int UG_CORR_COL = 128;
-constexpr int UG_A_PART = 16 * UG_SBO;
-constexpr int UG_B_PART = (UG_BN / 8) * UG_SBO;
-constexpr int UG_STAGE_BYTES = 2 * (UG_A_PART + UG_B_PART);
-constexpr int UG_SMEM = UG_STAGES * UG_STAGE_BYTES;      // 95 KB -> two CTAs per SM
+constexpr int UG_RAW_STAGE = UG_THREADS * 4 * 16;   // 4 x 16 B per thread per chunk (2 A + 2 B pieces)
+
+// shared-memory budget per GEMM form, sized so that two CTAs fit one SM (<= ~113 KB each)
+template <int MODE>
+struct UGLayout {
+  static constexpr bool A_KMAJ = (MODE != 2), B_KMAJ = (MODE == 0);
+  static constexpr int A_PART = 16 * UG_SBO;                 // 8448: both operands live in the K-major layout
+  static constexpr int B_PART = (UG_BN / 8) * UG_SBO;        // 7392
+  static constexpr int STAGE_BYTES = 2 * (A_PART + B_PART);
+  static constexpr int DEPTH = 3;                            // cp.async ring depth
+  static constexpr int SMEM = UG_STAGES * STAGE_BYTES + DEPTH * UG_RAW_STAGE;                  // 110 KB
+};
 
 struct UGemmArgs {
   const float* A; i64 lda;
@@ -39,126 +52,141 @@ struct UGemmArgs {
   int M, N, K;
   float alpha, beta;
   int act, splits;
+  int variant;         // debug: MN-major descriptor field assignment under test
+  long long* dbg;      // optional phase timestamps of CTA (0,0,0) thread 0 (profiling aid; nullptr in production)
 };
 
-struct OperandRegs {
-  float4 v[4];
-};
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int valid_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// ---- source rows are K-contiguous: element (r, k) at g[r*ld + k]; R rows (multiple of 8, <= 128) ------------
-template <int R>
-__device__ __forceinline__ void load_kmajor(OperandRegs& o, const float* __restrict__ g, i64 ld, int row0, int row_end,
-                                            int k0, int k_end, bool vec) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r_in = lane & 7, c = lane >> 3;
-  const int k = k0 + 4 * c;
+// One operand (A: 128 rows, B: UG_BN rows) as seen by one converter thread: two 16-byte pieces per K chunk.
+// Everything that does not depend on the chunk index is computed once; per chunk the thread only bumps two
+// pointers and selects "full" or "tail" byte counts, so the staging code is branch-free.
+//   KMAJ  (rows K-contiguous, element (r,k) at g[r*ld+k]):  piece i = row group (warp + 8 i), row lane&7, k-quad lane>>3
+//   !KMAJ (MN-contiguous,     element (r,k) at g[k*ld+r]):  piece i = k (warp + 8 i),         rows 4*lane .. 4*lane+3
+template <int R, bool KMAJ>
+struct OperandThread {
+  const char* ptr[2];     // source address of the piece for the next chunk to stage (always a readable address)
+  i64 stride[2];          // bytes between consecutive K chunks (0 for pieces outside the matrix)
+  int full[2], tail[2];   // valid bytes in a full chunk / in the last chunk
+  uint32_t raw_off[2];    // staging slot offset inside a ring stage
+  int st_off[2];          // destination offset inside an operand part (-1: this thread has no such piece)
+  int kofs[2];
+
+  __device__ __forceinline__ void init(const float* g, i64 ld, int row0, int row_end, int kb, int ke, int nchunks,
+                                       int slot_base) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k_last = kb + (nchunks - 1) * UG_KC;
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int rg = warp + 4 * i;
-    const int row = row0 + rg * 8 + r_in;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rg < R / 8 && row < row_end && k < k_end) {
-      const float* p = g + (i64)row * ld + k;
-      if (vec && k + 3 < k_end) {
-        v = *reinterpret_cast<const float4*>(p);
+    for (int i = 0; i < 2; i++) {
+      raw_off[i] = (uint32_t)(((slot_base + i) * UG_THREADS + threadIdx.x) * 16);
+      bool ok;
+      if (KMAJ) {
+        const int rg = warp + 8 * i, r_in = lane & 7, c = lane >> 3;
+        const int row = row0 + rg * 8 + r_in;
+        kofs[i] = 4 * c;
+        st_off[i] = (rg < R / 8) ? (rg * UG_SBO + c * UG_LBO + r_in * 16) : -1;
+        ok = (rg < R / 8) && (row < row_end);
+        ptr[i] = reinterpret_cast<const char*>(ok ? g + (i64)row * ld + kb + 4 * c : g);
+        stride[i] = ok ? (i64)UG_KC * 4 : 0;
+        full[i] = ok ? 16 : 0;
+        tail[i] = ok ? max(0, min(16, 4 * (ke - (k_last + 4 * c)))) : 0;
       } else {
-        v.x = p[0];
-        if (k + 1 < k_end) v.y = p[1];
-        if (k + 2 < k_end) v.z = p[2];
-        if (k + 3 < k_end) v.w = p[3];
+        const int kl = warp + 8 * i, r = 4 * lane;
+        const int row = row0 + r;
+        kofs[i] = kl;
+        st_off[i] = (r < R) ? ((r >> 3) * UG_SBO + (r & 7) * 16 + (kl >> 2) * UG_LBO + (kl & 3) * 4) : -1;
+        ok = (r < R) && (row < row_end);
+        ptr[i] = reinterpret_cast<const char*>(ok ? g + (i64)(kb + kl) * ld + row : g);
+        stride[i] = ok ? (i64)UG_KC * ld * 4 : 0;
+        full[i] = ok ? min(16, 4 * (row_end - row)) : 0;
+        tail[i] = (k_last + kl < ke) ? full[i] : 0;
       }
     }
-    o.v[i] = v;
   }
-}
 
-template <int R>
-__device__ __forceinline__ void store_kmajor(const OperandRegs& o, uint8_t* hi, uint8_t* lo) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r_in = lane & 7, c = lane >> 3;
+  // asynchronous copy of the next chunk into the staging ring
+  __device__ __forceinline__ void stage(bool is_last, uint32_t raw_base) {
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int rg = warp + 4 * i;
-    if (rg >= R / 8) continue;
-    const int off = rg * UG_SBO + c * UG_LBO + r_in * 16;
+    for (int i = 0; i < 2; i++) {
+      if (st_off[i] < 0) continue;                    // compile-time for R = 128, warp-uniform otherwise
+      cp_async16(raw_base + raw_off[i], ptr[i], is_last ? tail[i] : full[i]);
+      ptr[i] += stride[i];
+    }
+  }
+
+  // synchronous scalar read of chunk c (leading dimension not a multiple of 4 floats: no 16-byte alignment)
+  __device__ __forceinline__ float4 read_scalar(int i, bool is_last) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (st_off[i] < 0) return v;
+    const int nv = (is_last ? tail[i] : full[i]) >> 2;
+    const float* q = reinterpret_cast<const float*>(ptr[i]);
+    if (nv > 0) v.x = q[0];
+    if (nv > 1) v.y = q[1];
+    if (nv > 2) v.z = q[2];
+    if (nv > 3) v.w = q[3];
+    ptr[i] += stride[i];
+    return v;
+  }
+
+  // split the piece into tf32 hi/lo and write both halves into the UMMA operand stage
+  __device__ __forceinline__ void convert(int i, float4 v, uint8_t* hi, uint8_t* lo) const {
+    if (st_off[i] < 0) return;
     float4 h, l;
-    umma::split_tf32(o.v[i].x, h.x, l.x);
-    umma::split_tf32(o.v[i].y, h.y, l.y);
-    umma::split_tf32(o.v[i].z, h.z, l.z);
-    umma::split_tf32(o.v[i].w, h.w, l.w);
-    *reinterpret_cast<float4*>(hi + off) = h;
-    *reinterpret_cast<float4*>(lo + off) = l;
-  }
-}
-
-// ---- source is MN-contiguous: element (r, k) at g[k*ld + r]  (transposed on the way into shared memory) ----
-template <int R>
-__device__ __forceinline__ void load_mnmajor(OperandRegs& o, const float* __restrict__ g, i64 ld, int row0, int row_end,
-                                             int k0, int k_end, bool vec) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r = 4 * lane;
-  const int row = row0 + r;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int k = k0 + warp + 4 * i;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < R && k < k_end && row < row_end) {
-      const float* q = g + (i64)k * ld + row;
-      if (vec && row + 3 < row_end) {
-        v = *reinterpret_cast<const float4*>(q);
-      } else {
-        v.x = q[0];
-        if (row + 1 < row_end) v.y = q[1];
-        if (row + 2 < row_end) v.z = q[2];
-        if (row + 3 < row_end) v.w = q[3];
-      }
-    }
-    o.v[i] = v;
-  }
-}
-
-template <int R>
-__device__ __forceinline__ void store_mnmajor(const OperandRegs& o, uint8_t* hi, uint8_t* lo) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r = 4 * lane;
-  if (r >= R) return;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int kl = warp + 4 * i;                                   // k within the chunk
-    const int koff = (kl >> 2) * UG_LBO + (kl & 3) * 4;
-    const float e[4] = {o.v[i].x, o.v[i].y, o.v[i].z, o.v[i].w};
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int rr = r + q;
-      const int off = (rr >> 3) * UG_SBO + (rr & 7) * 16 + koff;
-      float h, l;
-      umma::split_tf32(e[q], h, l);
-      *reinterpret_cast<float*>(hi + off) = h;
-      *reinterpret_cast<float*>(lo + off) = l;
+    umma::split_tf32(v.x, h.x, l.x);
+    umma::split_tf32(v.y, h.y, l.y);
+    umma::split_tf32(v.z, h.z, l.z);
+    umma::split_tf32(v.w, h.w, l.w);
+    if (KMAJ) {
+      *reinterpret_cast<float4*>(hi + st_off[i]) = h;
+      *reinterpret_cast<float4*>(lo + st_off[i]) = l;
+    } else {
+      // 4 consecutive rows of the same k: rows r..r+3 sit 16 bytes apart inside one 8-row core matrix
+      const int o = st_off[i];
+      *reinterpret_cast<float*>(hi + o) = h.x;      *reinterpret_cast<float*>(lo + o) = l.x;
+      *reinterpret_cast<float*>(hi + o + 16) = h.y; *reinterpret_cast<float*>(lo + o + 16) = l.y;
+      *reinterpret_cast<float*>(hi + o + 32) = h.z; *reinterpret_cast<float*>(lo + o + 32) = l.z;
+      *reinterpret_cast<float*>(hi + o + 48) = h.w; *reinterpret_cast<float*>(lo + o + 48) = l.w;
     }
   }
-}
+};
 
 // MODE 0: NT (A[M,K], B[N,K])   1: NN (A[M,K], B[K,N])   2: TN (A[K,M], B[K,N])
 template <int MODE>
-__global__ void __launch_bounds__(UG_THREADS, 2) umma_gemm_kernel(UGemmArgs p) {
+__global__ void __launch_bounds__(UG_ALL_THREADS, 2) umma_gemm_kernel(UGemmArgs p) {
   constexpr int BN = UG_BN;
+  using LY = UGLayout<MODE>;
+  constexpr bool A_KMAJ = LY::A_KMAJ, B_KMAJ = LY::B_KMAJ;
+  constexpr int UG_A_PART = LY::A_PART, UG_B_PART = LY::B_PART, UG_STAGE_BYTES = LY::STAGE_BYTES, UG_DEPTH = LY::DEPTH;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_free[UG_STAGES];
+  __shared__ __align__(8) uint64_t bar_free[UG_STAGES];   // tensor core -> converters: stage may be overwritten
+  __shared__ __align__(8) uint64_t bar_full[UG_STAGES];   // converters -> issuer: stage holds chunk c (256 arrivals)
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+  const bool dbg_on = p.dbg != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  int dbg_n = 0;
+#define UG_STAMP() do { if (dbg_on && dbg_n < 120) p.dbg[dbg_n++] = clock64(); } while (0)
+  UG_STAMP();
 
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, UG_TMEM_COLS);
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < UG_STAGES; s++) umma::mbar_init(&bar_free[s], 1);
+    for (int s = 0; s < UG_STAGES; s++) {
+      umma::mbar_init(&bar_free[s], 1);
+      umma::mbar_init(&bar_full[s], UG_THREADS);
+    }
     umma::fence_barrier_init();
   }
   umma::tc_fence_before_sync();
   __syncthreads();
   umma::tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
+  UG_STAMP();
 
   int kb = 0, ke = p.K;
   if (p.splits > 1) {
@@ -170,70 +198,103 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gemm_kernel(UGemmArgs p) {
 
   const bool a_vec = ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
   const bool b_vec = ((p.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0);
-  auto load_chunk = [&](int c, OperandRegs& ra, OperandRegs& rb) {
-    const int k0 = kb + c * UG_KC;
-    if (MODE == 2) load_mnmajor<128>(ra, p.A, p.lda, m0, p.M, k0, ke, a_vec);
-    else load_kmajor<128>(ra, p.A, p.lda, m0, p.M, k0, ke, a_vec);
-    if (MODE == 0) load_kmajor<BN>(rb, p.B, p.ldb, n0, p.N, k0, ke, b_vec);
-    else load_mnmajor<BN>(rb, p.B, p.ldb, n0, p.N, k0, ke, b_vec);
-  };
-  auto store_chunk = [&](int s, const OperandRegs& ra, const OperandRegs& rb) {
-    uint8_t* st = smem + s * UG_STAGE_BYTES;
-    if (MODE == 2) store_mnmajor<128>(ra, st, st + UG_A_PART);
-    else store_kmajor<128>(ra, st, st + UG_A_PART);
-    if (MODE == 0) store_kmajor<BN>(rb, st + 2 * UG_A_PART, st + 2 * UG_A_PART + UG_B_PART);
-    else store_mnmajor<BN>(rb, st + 2 * UG_A_PART, st + 2 * UG_A_PART + UG_B_PART);
-  };
   constexpr uint32_t IDESC = umma::idesc_tf32(128, BN);
 
-  // one pipeline step: stage chunk c (already in registers), refill the registers with chunk c+2, hand the stage to the tensor core
-  auto step = [&](int c, OperandRegs& ra, OperandRegs& rb) {
-    const int s = c % UG_STAGES;
-    if (c >= UG_STAGES) umma::mbar_wait(&bar_free[s], (uint32_t)(((c / UG_STAGES) - 1) & 1));   // MMAs of chunk c-3 released stage s
-    store_chunk(s, ra, rb);
-    if (c + 2 < nchunks) load_chunk(c + 2, ra, rb);      // two chunks in flight in registers
-    umma::fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      umma::tc_fence_after_sync();
-      const uint32_t base = umma::smem_u32(smem + s * UG_STAGE_BYTES);
-      const int kleft = ke - (kb + c * UG_KC);
-      const int ksteps = kleft >= UG_KC ? UG_KC / 8 : (kleft + 7) / 8;
-      for (int j = 0; j < ksteps; j++) {
-        const uint64_t a_hi = umma::smem_desc(base + j * 2 * UG_LBO, UG_LBO, UG_SBO);
-        const uint64_t a_lo = umma::smem_desc(base + UG_A_PART + j * 2 * UG_LBO, UG_LBO, UG_SBO);
-        const uint64_t b_hi = umma::smem_desc(base + 2 * UG_A_PART + j * 2 * UG_LBO, UG_LBO, UG_SBO);
-        const uint64_t b_lo = umma::smem_desc(base + 2 * UG_A_PART + UG_B_PART + j * 2 * UG_LBO, UG_LBO, UG_SBO);
-        const uint32_t first = (c > 0 || j > 0) ? 1u : 0u;
-        // the large hi*hi term and the 2^-11-scaled corrections accumulate in separate TMEM tiles, so the tensor
-        // core's truncating fp32 accumulate touches the main sum once per k-step instead of three times
-        umma::mma_tf32(tmem, a_hi, b_hi, IDESC, first);
-        umma::mma_tf32(tmem + UG_CORR_COL, a_lo, b_hi, IDESC, first);
-        umma::mma_tf32(tmem + UG_CORR_COL, a_hi, b_lo, IDESC, 1u);
+  if (warp == 8) {
+    // ===== MMA issuer: one thread feeds the tensor core as soon as a stage is full; it never touches operand data =====
+    if (lane == 0) {
+      for (int c = 0; c < nchunks; c++) {
+        const int s = c % UG_STAGES;
+        umma::mbar_wait(&bar_full[s], (uint32_t)((c / UG_STAGES) & 1));
+        umma::tc_fence_after_sync();
+        const uint32_t base = umma::smem_u32(smem + s * UG_STAGE_BYTES);
+        const int kleft = ke - (kb + c * UG_KC);
+        const int ksteps = kleft >= UG_KC ? UG_KC / 8 : (kleft + 7) / 8;
+        for (int j = 0; j < ksteps; j++) {
+          const uint64_t a_hi = umma::smem_desc(base + j * 2 * UG_LBO, UG_LBO, UG_SBO);
+          const uint64_t a_lo = umma::smem_desc(base + UG_A_PART + j * 2 * UG_LBO, UG_LBO, UG_SBO);
+          const uint64_t b_hi = umma::smem_desc(base + 2 * UG_A_PART + j * 2 * UG_LBO, UG_LBO, UG_SBO);
+          const uint64_t b_lo = umma::smem_desc(base + 2 * UG_A_PART + UG_B_PART + j * 2 * UG_LBO, UG_LBO, UG_SBO);
+          const uint32_t first = (c > 0 || j > 0) ? 1u : 0u;
+          // the large hi*hi term and the 2^-11-scaled corrections accumulate in separate TMEM tiles, so the tensor
+          // core's truncating fp32 accumulate touches the main sum once per k-step instead of three times
+          umma::mma_tf32(tmem, a_hi, b_hi, IDESC, first);
+          umma::mma_tf32(tmem + UG_CORR_COL, a_lo, b_hi, IDESC, first);
+          umma::mma_tf32(tmem + UG_CORR_COL, a_hi, b_lo, IDESC, 1u);
+        }
+        umma::mma_commit(&bar_free[s]);
       }
-      umma::mma_commit(&bar_free[s]);
     }
+    umma::tc_fence_before_sync();
+    __syncthreads();           // matches the converters' final barrier before the TMEM is released
+    return;
+  }
+
+  // ===== converters (warps 0-7): global -> (cp.async ring) -> registers -> tf32 hi/lo -> UMMA operand stage =====
+  OperandThread<128, A_KMAJ> oa;
+  OperandThread<BN, B_KMAJ> ob;
+  oa.init(p.A, p.lda, m0, p.M, kb, ke, nchunks, 0);
+  ob.init(p.B, p.ldb, n0, p.N, kb, ke, nchunks, 2);
+  const uint32_t raw_u32 = umma::smem_u32(smem + UG_STAGES * UG_STAGE_BYTES);
+  uint8_t* const raw_ptr = smem + UG_STAGES * UG_STAGE_BYTES;
+
+  int ring_w = 0;                       // ring stage the next staged chunk goes to
+  auto stage_chunk = [&](int c) {
+    if (c < nchunks) {
+      const bool is_last = (c == nchunks - 1);
+      const uint32_t rb = raw_u32 + (uint32_t)(ring_w * UG_RAW_STAGE);
+      if (a_vec) oa.stage(is_last, rb);
+      if (b_vec) ob.stage(is_last, rb);
+    }
+    ring_w = (ring_w + 1 == UG_DEPTH) ? 0 : ring_w + 1;
+    cp_async_commit();         // always: keeps the group count uniform
   };
 
-  OperandRegs ra0, rb0, ra1, rb1;
-  if (nchunks > 0) load_chunk(0, ra0, rb0);
-  if (nchunks > 1) load_chunk(1, ra1, rb1);
-  for (int c = 0; c < nchunks; c += 2) {
-    step(c, ra0, rb0);
-    if (c + 1 < nchunks) step(c + 1, ra1, rb1);
+#pragma unroll
+  for (int c = 0; c < UG_DEPTH - 1; c++) stage_chunk(c);
+  int ring_r = 0, s = 0;
+  uint32_t free_parity = 1;             // parity to wait for on bar_free[s]; flips every time s wraps (first use: no wait)
+  for (int c = 0; c < nchunks; c++) {
+    const bool is_last = (c == nchunks - 1);
+    stage_chunk(c + UG_DEPTH - 1);
+    cp_async_wait<UG_DEPTH - 1>();                        // this thread's pieces of chunk c have landed
+    UG_STAMP();
+    const uint8_t* raw = raw_ptr + ring_r * UG_RAW_STAGE;
+    float4 va[2], vb[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      va[i] = a_vec ? *reinterpret_cast<const float4*>(raw + oa.raw_off[i]) : oa.read_scalar(i, is_last);
+      vb[i] = b_vec ? *reinterpret_cast<const float4*>(raw + ob.raw_off[i]) : ob.read_scalar(i, is_last);
+    }
+    if (c >= UG_STAGES) umma::mbar_wait(&bar_free[s], free_parity);   // MMAs of chunk c-2 released stage s
+    UG_STAMP();
+    uint8_t* st = smem + s * UG_STAGE_BYTES;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      oa.convert(i, va[i], st, st + UG_A_PART);
+      ob.convert(i, vb[i], st + 2 * UG_A_PART, st + 2 * UG_A_PART + UG_B_PART);
+    }
+    umma::fence_proxy_async_smem();                       // my generic-proxy writes -> visible to the tensor core
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(&bar_full[s])) : "memory");
+    UG_STAMP();
+    ring_r = (ring_r + 1 == UG_DEPTH) ? 0 : ring_r + 1;
+    if (++s == UG_STAGES) { s = 0; free_parity ^= 1; }
   }
+  cp_async_wait<0>();
   if (nchunks > 0) {
     const int last = nchunks - 1;
     umma::mbar_wait(&bar_free[last % UG_STAGES], (uint32_t)((last / UG_STAGES) & 1));
   }
   umma::tc_fence_after_sync();
+  UG_STAMP();
 
-  // ---- epilogue: thread = output row (TMEM lane), 16 columns per tcgen05.ld ----
-  const int row = m0 + warp * 32 + lane;
-  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  // ---- epilogue: thread = output row (TMEM lane 32*(warp%4)+lane); warps 0-3 take column chunks 0..3, warps 4-7 chunks 4..6 ----
+  const int row = m0 + (warp & 3) * 32 + lane;
+  const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const bool c_vec = (p.splits <= 1) && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+  const int cb_begin = (warp < 4) ? 0 : 64, cb_end = (warp < 4) ? 64 : BN;
 #pragma unroll 1
-  for (int cb = 0; cb < BN; cb += 16) {
+  for (int cb = cb_begin; cb < cb_end; cb += 16) {
     if (n0 + cb >= p.N) break;                      // warp-uniform
     float v[16];
     if (nchunks > 0) {
@@ -277,9 +338,13 @@ __global__ void __launch_bounds__(UG_THREADS, 2) umma_gemm_kernel(UGemmArgs p) {
       }
     }
   }
+  UG_STAMP();
   umma::tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, UG_TMEM_COLS);
+  UG_STAMP();
+  if (dbg_on) p.dbg[127] = dbg_n;
+#undef UG_STAMP
 }
 
 __global__ void ug_scale2d_kernel(float* C, i64 ldc, int M, int N, float beta) {
@@ -294,14 +359,17 @@ template <int MODE>
 static int launch_umma(const UGemmArgs& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    MMDFN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, UG_SMEM));
+    MMDFN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, UGLayout<MODE>::SMEM));
     configured = true;
   }
   dim3 grid(ceil_div(p.M, 128), ceil_div(p.N, UG_BN), p.splits > 1 ? p.splits : 1);
-  umma_gemm_kernel<MODE><<<grid, UG_THREADS, UG_SMEM, st>>>(p);
+  umma_gemm_kernel<MODE><<<grid, UG_ALL_THREADS, UGLayout<MODE>::SMEM, st>>>(p);
   MMDFN_LAUNCH_CHECK();
   return 0;
 }
+
+static long long* g_ug_dbg = nullptr;
+static int g_ug_variant = 0;
 
 int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64 lda, const float* B, i64 ldb,
               float beta, float* C, i64 ldc, const float* bias, int act, cudaStream_t st) {
@@ -309,7 +377,7 @@ int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A
   if (M == 0 || N == 0) return 0;
   if (!A || !B || !C) return MMDFN_ENULL;
   if (tb && ta) return MMDFN_EINVAL;
-  UGemmArgs p{A, lda, B, ldb, C, ldc, bias, M, N, K, alpha, beta, act, 1};
+  UGemmArgs p{A, lda, B, ldb, C, ldc, bias, M, N, K, alpha, beta, act, 1, g_ug_variant, g_ug_dbg};
   const i64 tiles = (i64)ceil_div(M, 128) * ceil_div(N, UG_BN);
   // split the contraction when the output has fewer tiles than two waves of 2 CTAs/SM (weight gradients)
   if (tiles < 296 && K >= 512 && bias == nullptr && act == 0) {
@@ -328,6 +396,17 @@ int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A
 }
 
 }  // namespace mmdfn
+
+// profiling aid: device buffer of 128 int64 receiving clock64() phase stamps of CTA 0 (nullptr switches it off)
+extern "C" int mmdfn_gemm_tc_set_debug(long long* device_buf) {
+  mmdfn::g_ug_dbg = device_buf;
+  return 0;
+}
+
+extern "C" int mmdfn_gemm_tc_set_variant(int v) {
+  mmdfn::g_ug_variant = v;
+  return 0;
+}
 
 extern "C" int mmdfn_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
                              const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias,

@@ -1,0 +1,61 @@
+// Layout probe (debug aid, not on any product path): one tcgen05.mma with A = identity on the first 8 rows/k
+// (K-major, known-good) and the B operand region filled with its own word offsets.  D[k][n] then reads back the
+// shared-memory word the tensor core uses as B(k, n) for a given descriptor (lbo, sbo) and major-ness.
+#include "umma.cuh"
+
+namespace mmdfn {
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(float* out, int N, int lbo, int sbo, int b_mn, int probe_a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* ident = reinterpret_cast<float*>(smem);                 // 16 KB: identity operand, K-major (SBO 528, LBO 128)
+  float* probe = reinterpret_cast<float*>(smem + 16384);         // 48 KB: word-offset pattern
+  for (int i = tid; i < 4096; i += 128) ident[i] = 0.f;
+  for (int i = tid; i < 12288; i += 128) probe[i] = (float)i;
+  __syncthreads();
+  if (tid < 8) ident[(tid * 16 + (tid >> 2) * 128 + (tid & 3) * 4) / 4] = 1.0f;   // element (r=tid, k=tid) of row group 0
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 256);
+  if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_barrier_init(); }
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint64_t d_ident = umma::smem_desc(umma::smem_u32(ident), 128, 528);
+    const uint64_t d_probe = umma::smem_desc(umma::smem_u32(probe), (uint32_t)lbo, (uint32_t)sbo);
+    if (!probe_a) {
+      // D[m][n] = sum_k I[m][k] * P(k, n)  ->  rows 0..7 show P(k = m, n)
+      umma::mma_tf32(tmem, d_ident, d_probe, umma::idesc_tf32(128, N, 0, b_mn), 0u);
+    } else {
+      // D[m][n] = sum_k P(m, k) * I[n][k]  ->  columns 0..7 show P(m, k = n)
+      umma::mma_tf32(tmem, d_probe, d_ident, umma::idesc_tf32(128, N, b_mn, 0), 0u);
+    }
+    umma::mma_commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::tc_fence_after_sync();
+  const int row = warp * 32 + lane;
+  for (int cb = 0; cb < N; cb += 16) {
+    float v[16];
+    umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + cb, v);
+    for (int q = 0; q < 16; q++) out[row * N + cb + q] = v[q];
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
+}
+}  // namespace mmdfn
+
+extern "C" int mmdfn_umma_probe(float* out, int N, int lbo, int sbo, int mn_major, int probe_a, void* stream) {
+  using namespace mmdfn;
+  static bool configured = false;
+  if (!configured) {
+    MMDFN_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    configured = true;
+  }
+  umma_probe_kernel<<<1, 128, 65536, (cudaStream_t)stream>>>(out, N, lbo, sbo, mn_major, probe_a);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
