@@ -34,6 +34,13 @@ class BlockAdj:
         return (3 * self.geom.N, 3 * self.geom.N)
 
 
+def _side_stream(device, cache={}):
+    key = str(device)
+    if key not in cache:
+        cache[key] = torch.cuda.Stream(device=device)
+    return cache[key]
+
+
 def _geom_of(lengths, device, cache={}):
     key = (tuple(int(x) for x in lengths), str(device))
     g = cache.get(key)
@@ -370,8 +377,16 @@ class DialogueGNNModel(nn.Module):
         # k1: the three projections into one stacked table (a, v, l)
         Utab = ops.Proj3Fn.apply(U_a, U_v, U, self.linear_a.weight, self.linear_a.bias, self.linear_v.weight,
                                  self.linear_v.bias, self.linear_l.weight, self.linear_l.bias)
-        # k2: text BiGRU over the padded sequence
-        E_l = ops.BiGRU2Fn.apply(Utab[2].reshape(T * B, 200), None, T, B, m_l, scale, *self._gru_weights(self.lstm_l))
+        # k2: text BiGRU over the padded sequence.  It is independent of the speaker-party encoder below and both are
+        # few-CTA, latency-bound recurrences, so it runs on a side stream (autograd replays the same stream in backward).
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if self.use_crn_speaker else None
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                E_l = ops.BiGRU2Fn.apply(Utab[2].reshape(T * B, 200), None, T, B, m_l, scale, *self._gru_weights(self.lstm_l))
+        else:
+            E_l = ops.BiGRU2Fn.apply(Utab[2].reshape(T * B, 200), None, T, B, m_l, scale, *self._gru_weights(self.lstm_l))
         Q = sel = pos = None
         if self.use_crn_speaker:
             # k3: shared speaker-party BiGRU over all (modality, dialogue, speaker) sequences at once
@@ -380,6 +395,9 @@ class DialogueGNNModel(nn.Module):
             m_p = ops.make_mask((T, nseq, 200), p, dev) if train_drop else mk.get("gru_p")
             Q = ops.BiGRU2Fn.apply(Utab.reshape(3 * T * B, 200), rowmap, T, nseq, m_p, scale,
                                    *self._gru_weights(self.rnn_parties))
+        if side is not None:
+            main.wait_stream(side)
+            E_l.record_stream(main)
         # k3/k4: scatter + speaker-weight combine + ragged pack, written as the stacked graph input
         X = ops.PartyPackFn.apply(Utab, E_l, Q, geom, sel, pos, S, tuple(self.speaker_weights))
         gm = mk.get("gcn") if masks is not None else None
