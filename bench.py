@@ -183,12 +183,12 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def roofline_graph_conv(dev):
+def roofline_graph_conv(dev, n_dialogues=DIALOGUES_PER_GPU):
     """k6 message aggregate hi = A_hat z on the bench shard, timed alone with CUDA events on the launching
     stream; operands rotate over enough copies to defeat the 126 MB L2."""
     from mmdfn_b200 import ops
     from mmdfn_b200._lib import call, ptr, stream
-    lengths = [UTT] * DIALOGUES_PER_GPU
+    lengths = [UTT] * n_dialogues
     geom = ops.DialogGeom(lengths, dev)
     N, G = geom.N, 100
     alg_bytes = 4 * (3 * N * G + 3 * N * G + sum(3 * L * L + 3 * L for L in lengths))     # z in, hi out, A_hat blocks + diagonals
@@ -219,7 +219,7 @@ def roofline_graph_conv(dev):
     return {"kernel": "adj_spmm_kernel (k6 graph-conv message aggregate hi = A_hat z, fp32)", "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us, "peak_source": how,
-            "note": "launch covers one GCN layer of the 32x100 shard; operands rotated over %d copies (> L2)" % copies}
+            "note": "launch covers one GCN layer of the %dx100 shard; operands rotated over %d copies (> L2)" % (n_dialogues, copies)}
 
 
 def main():
@@ -327,6 +327,8 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall}
         try:
             line["roofline"] = roofline_graph_conv(dev)
+            big = roofline_graph_conv(dev, 256)          # BASELINE config 4 on one GPU (256 x 100 utterances): steady-state view
+            line["roofline"]["at_256_dialogues"] = {k: big[k] for k in ("achieved", "frac", "us_per_launch", "algorithmic_bytes_per_launch")}
         except Exception as e:  # pragma: no cover
             line["roofline"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:

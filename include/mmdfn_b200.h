@@ -68,10 +68,14 @@ long long mmdfn_bigru2_ws_floats(int T, int nseq, long long rows);
 int mmdfn_bigru2_fwd(int T, int nseq, long long rows, const float* x, const int* rowmap, const float* const* w,
                      const unsigned char* mask, float mask_scale, float* y2, float* ws, void* stream);
 long long mmdfn_bigru2_bwd_ws_floats(int T, int nseq, long long rows);
-/* dx (rows,200): "=" or "+=" (accumulate_dx), may be NULL; dw: 16 gradient pointers ("="). */
+/* dx (rows,200): "=" or "+=" (accumulate_dx), may be NULL; dw: 16 gradient pointers.  dw_zeroed != 0: the caller
+ * zero-filled them (one memset of a shared buffer) and gradients are accumulated, which saves the zero-init
+ * launches of the split-K GEMMs; when weight_ih_l{k} and weight_ih_l{k}_reverse gradients are adjacent in memory
+ * both directions are computed by one GEMM. */
 int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x, const int* rowmap, const float* const* w,
                      const unsigned char* mask, float mask_scale, const float* y2, const float* dy2,
-                     const float* ws_fwd, float* dx, int accumulate_dx, float* const* dw, float* ws, void* stream);
+                     const float* ws_fwd, float* dx, int accumulate_dx, float* const* dw, int dw_zeroed, float* ws,
+                     void* stream);
 
 /* ---- k3/k4: speaker-party partition + fused scatter/combine/ragged pack ------------------------
  * code/model.py:1070-1090, 1101-1121, 1134-1154 and simple_batch_graphify :553-565.

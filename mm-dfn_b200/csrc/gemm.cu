@@ -109,7 +109,7 @@ int gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64
     p.splits = (int)(s < smax ? s : smax);
     if (p.splits < 1) p.splits = 1;
   }
-  if (p.splits > 1) {
+  if (p.splits > 1 && beta != 1.f) {
     const i64 tot = (i64)M * N;
     scale2d_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(C, ldc, M, N, beta);
     MMDFN_LAUNCH_CHECK();

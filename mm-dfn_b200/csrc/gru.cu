@@ -125,8 +125,10 @@ struct GruBwdArgs {
   const float* y;       // (T, nseq, 200)
   const float* gates;   // (T, nseq, 2, 400)
   const float* w_hh[2];
-  float* dxg;           // (T, nseq, 2, 300)  d/d(input gates)  = [dr_pre dz_pre dn_pre]
-  float* dhn;           // (T, nseq, 2, 100)  d/d(W_hn h + b_hn) = dn_pre * r
+  float* dxg;           // (T, nseq, 2, 300)  d/d(input gates)     = [dr_pre dz_pre dn_pre]
+  float* dgh;           // (T, nseq, 2, 300)  d/d(W_hh h + b_hh)   = [dr_pre dz_pre dn_pre*r]
+  float* db_ih[2];      // (300) per direction, pre-zeroed: column sums of dxg, accumulated here (atomics)
+  float* db_hh[2];      // (300) per direction, pre-zeroed: column sums of dgh
 };
 
 template <int NB>
@@ -168,6 +170,9 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(GruBwdArgs p) {
       }
     }
   };
+  float sb[ITEMS][4];                                  // running bias-gradient sums of this thread's (b, u) items
+#pragma unroll
+  for (int it = 0; it < ITEMS; it++) sb[it][0] = sb[it][1] = sb[it][2] = sb[it][3] = 0.f;
   fetch(0, cur);
   for (int step = 0; step < p.T; step++) {
     const int t = dir ? step : (p.T - 1 - step);
@@ -187,9 +192,11 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(GruBwdArgs p) {
       const float dhn_ = dn_pre * r;
       float* o = p.dxg + (slot * 2 + dir) * G3;
       o[u] = dr_pre; o[GH + u] = dz_pre; o[2 * GH + u] = dn_pre;
-      p.dhn[(slot * 2 + dir) * GH + u] = dhn_;
+      float* o2 = p.dgh + (slot * 2 + dir) * G3;
+      o2[u] = dr_pre; o2[GH + u] = dz_pre; o2[2 * GH + u] = dhn_;
       dgh[b][u] = dr_pre; dgh[b][GH + u] = dz_pre; dgh[b][2 * GH + u] = dhn_;
       dh[b][u] = dht * z;
+      sb[it][0] += dr_pre; sb[it][1] += dz_pre; sb[it][2] += dn_pre; sb[it][3] += dhn_;
     }
     fetch(step + 1, nxt);                              // lands while the mat-vec below runs
     __syncthreads();
@@ -214,6 +221,19 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(GruBwdArgs p) {
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < ITEMS; it++) cur[it] = nxt[it];
+  }
+  // bias gradients: one atomic per (item, gate) per CTA
+#pragma unroll
+  for (int it = 0; it < ITEMS; it++) {
+    const int idx = tid + it * GRU_THREADS;
+    if (idx >= nb * GH) continue;
+    const int u = idx % GH;
+    atomicAdd(p.db_ih[dir] + u, sb[it][0]);
+    atomicAdd(p.db_ih[dir] + GH + u, sb[it][1]);
+    atomicAdd(p.db_ih[dir] + 2 * GH + u, sb[it][2]);
+    atomicAdd(p.db_hh[dir] + u, sb[it][0]);
+    atomicAdd(p.db_hh[dir] + GH + u, sb[it][1]);
+    atomicAdd(p.db_hh[dir] + 2 * GH + u, sb[it][3]);
   }
 }
 
@@ -307,32 +327,31 @@ extern "C" int mmdfn_bigru2_fwd(int T, int nseq, long long rows, const float* x,
 
 extern "C" long long mmdfn_bigru2_bwd_ws_floats(int T, int nseq, long long rows) {
   const i64 slots = (i64)T * nseq;
-  // dxg (slots*600) | dhn (slots*200) | dy1 (slots*200) | dG (rows*600)
-  return slots * (600 + 200 + 200) + rows * 600;
+  // dxg (slots*600) | dgh (slots*600) | dy1 (slots*200) | dG (rows*600)
+  return slots * (600 + 600 + 200) + rows * 600;
 }
 
-// One layer's weight gradients from dxg/dhn.  xin: the layer input rows (ld 200) matching the
-// rows of dgate (ld 600); yl: that layer's output (T, nseq, 200).
-static int gru_layer_wgrads(int T, int nseq, i64 in_rows, const float* dgate_in, const float* xin, const float* dxg,
-                            const float* dhn, const float* yl, float* const* dw, int base, cudaStream_t st) {
-  const i64 slots = (i64)T * nseq;
+// One layer's weight gradients.  dgate_in: (in_rows, 600) gradient w.r.t. the input gates of the rows of `xin`
+// (ld 200); dgh: (T*nseq, 600); yl: that layer's output (T, nseq, 200).  Bias gradients were accumulated by the
+// recurrence kernel.  beta = 1 when the caller pre-zeroed the gradient buffers (no zero-init launches).
+static int gru_layer_wgrads(int T, int nseq, i64 in_rows, const float* dgate_in, const float* xin, const float* dgh,
+                            const float* yl, float* const* dw, int base, float beta, cudaStream_t st) {
   const i64 mprev = (i64)(T - 1) * nseq;
+  float* dW_ih_f = dw[base + 0];
+  float* dW_ih_b = dw[base + 4];
+  if (dW_ih_b == dW_ih_f + 300 * 200) {
+    // both directions in one GEMM: [dW_ih_f; dW_ih_b] (600,200) = dgate_in^T xin
+    MMDFN_TRY(gemm(true, false, 600, 200, (int)in_rows, 1.f, dgate_in, 600, xin, 200, beta, dW_ih_f, 200, nullptr, 0, st));
+  } else {
+    MMDFN_TRY(gemm(true, false, 300, 200, (int)in_rows, 1.f, dgate_in, 600, xin, 200, beta, dW_ih_f, 200, nullptr, 0, st));
+    MMDFN_TRY(gemm(true, false, 300, 200, (int)in_rows, 1.f, dgate_in + 300, 600, xin, 200, beta, dW_ih_b, 200, nullptr, 0, st));
+  }
   for (int d = 0; d < 2; d++) {
-    float* dW_ih = dw[base + 4 * d + 0];
     float* dW_hh = dw[base + 4 * d + 1];
-    float* db_ih = dw[base + 4 * d + 2];
-    float* db_hh = dw[base + 4 * d + 3];
-    // dW_ih (300,200) = dgate_in[:, d]^T xin
-    MMDFN_TRY(gemm(true, false, 300, 200, (int)in_rows, 1.f, dgate_in + d * 300, 600, xin, 200, 0.f, dW_ih, 200, nullptr, 0, st));
-    MMDFN_TRY(colsum((int)slots, 300, dxg + d * 300, 600, 0.f, db_ih, st));
     // h_prev of slot t is y[t-1] (forward direction) / y[t+1] (reverse direction)
-    const float* A_rz = d == 0 ? dxg + (i64)nseq * 600 : dxg + 300;
-    const float* A_n = d == 0 ? dhn + (i64)nseq * 200 : dhn + 100;
+    const float* Ag = d == 0 ? dgh + (i64)nseq * 600 : dgh + 300;
     const float* Bh = d == 0 ? yl : yl + (i64)nseq * 200 + 100;
-    MMDFN_TRY(gemm(true, false, 200, 100, (int)mprev, 1.f, A_rz, 600, Bh, 200, 0.f, dW_hh, 100, nullptr, 0, st));
-    MMDFN_TRY(gemm(true, false, 100, 100, (int)mprev, 1.f, A_n, 200, Bh, 200, 0.f, dW_hh + 200 * 100, 100, nullptr, 0, st));
-    MMDFN_TRY(colsum((int)slots, 200, dxg + d * 300, 600, 0.f, db_hh, st));
-    MMDFN_TRY(colsum((int)slots, 100, dhn + d * 100, 200, 0.f, db_hh + 200, st));
+    MMDFN_TRY(gemm(true, false, 300, 100, (int)mprev, 1.f, Ag, 600, Bh, 200, beta, dW_hh, 100, nullptr, 0, st));
   }
   return 0;
 }
@@ -340,7 +359,7 @@ static int gru_layer_wgrads(int T, int nseq, i64 in_rows, const float* dgate_in,
 extern "C" int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x, const int* rowmap,
                                 const float* const* w, const unsigned char* mask, float mask_scale, const float* y2,
                                 const float* dy2, const float* ws_fwd, float* dx, int accumulate_dx,
-                                float* const* dw, float* ws, void* stream) {
+                                float* const* dw, int dw_zeroed, float* ws, void* stream) {
   if (!x || !w || !y2 || !dy2 || !ws_fwd || !dw || !ws) return MMDFN_ENULL;
   if (!rowmap && rows != (i64)T * nseq) return MMDFN_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
@@ -353,13 +372,19 @@ extern "C" int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x,
   const float* gates2 = gates1 + slots * 800 + slots * 600;
   const float* l1in = mask ? y1d : y1;
   float* dxg = ws;
-  float* dhn = dxg + slots * 600;
-  float* dy1 = dhn + slots * 200;
+  float* dgh = dxg + slots * 600;
+  float* dy1 = dgh + slots * 600;
   float* dG = dy1 + slots * 200;
+  const float wbeta = dw_zeroed ? 1.f : 0.f;
+  if (!dw_zeroed) {
+    for (int i = 0; i < 16; i++) {
+      if ((i & 3) >= 2) MMDFN_TRY(fill_zero(dw[i], 300 * sizeof(float), st));       // bias gradients are accumulated with atomics
+    }
+  }
   // ---- layer 1 ----
-  GruBwdArgs b{T, nseq, dy2, y2, gates2, {w[9], w[13]}, dxg, dhn};
+  GruBwdArgs b{T, nseq, dy2, y2, gates2, {w[9], w[13]}, dxg, dgh, {dw[10], dw[14]}, {dw[11], dw[15]}};
   MMDFN_TRY(launch_gru_bwd(b, st));
-  MMDFN_TRY(gru_layer_wgrads(T, nseq, slots, dxg, l1in, dxg, dhn, y2, dw, 8, st));
+  MMDFN_TRY(gru_layer_wgrads(T, nseq, slots, dxg, l1in, dgh, y2, dw, 8, wbeta, st));
   MMDFN_TRY(gemm(false, false, (int)slots, 200, 300, 1.f, dxg, 600, w[8], 200, 0.f, dy1, 200, nullptr, 0, st));
   MMDFN_TRY(gemm(false, false, (int)slots, 200, 300, 1.f, dxg + 300, 600, w[12], 200, 1.f, dy1, 200, nullptr, 0, st));
   if (mask) {
@@ -367,7 +392,7 @@ extern "C" int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x,
     MMDFN_LAUNCH_CHECK();
   }
   // ---- layer 0 ----
-  GruBwdArgs a{T, nseq, dy1, y1, gates1, {w[1], w[5]}, dxg, dhn};
+  GruBwdArgs a{T, nseq, dy1, y1, gates1, {w[1], w[5]}, dxg, dgh, {dw[2], dw[6]}, {dw[3], dw[7]}};
   MMDFN_TRY(launch_gru_bwd(a, st));
   const float* dgate_in = dxg;
   if (rowmap) {
@@ -376,7 +401,7 @@ extern "C" int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x,
     MMDFN_LAUNCH_CHECK();
     dgate_in = dG;
   }
-  MMDFN_TRY(gru_layer_wgrads(T, nseq, rows, dgate_in, x, dxg, dhn, y1, dw, 0, st));
+  MMDFN_TRY(gru_layer_wgrads(T, nseq, rows, dgate_in, x, dgh, y1, dw, 0, wbeta, st));
   if (dx) {
     const float beta = accumulate_dx ? 1.f : 0.f;
     MMDFN_TRY(gemm(false, false, (int)rows, 200, 300, 1.f, dgate_in, 600, w[0], 200, beta, dx, 200, nullptr, 0, st));

@@ -386,7 +386,7 @@ int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A
     p.splits = (int)(s < smax ? s : smax);
     if (p.splits < 1) p.splits = 1;
   }
-  if (p.splits > 1) {
+  if (p.splits > 1 && beta != 1.f) {
     ug_scale2d_kernel<<<(unsigned)ceil_div64((i64)M * N, 256), 256, 0, st>>>(C, ldc, M, N, beta);
     MMDFN_LAUNCH_CHECK();
   }

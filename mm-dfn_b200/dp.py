@@ -49,11 +49,13 @@ class FlatAdamTrainer:
         self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
         off = 0
+        self.params, self.grad_views = params, []
         for p in params:
             n = p.numel()
             self.flat_p[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off:off + n].view_as(p)          # parameters become views of the bucket
-            p.grad = self.flat_g[off:off + n].view_as(p)          # autograd accumulates in place into the bucket
+            self.grad_views.append(self.flat_g[off:off + n].view_as(p))
+            p.grad = None
             off += n
         self.total = total
         self.step_count = 0
@@ -63,13 +65,15 @@ class FlatAdamTrainer:
     def step(self, textf, qmask, umask, lengths, acouf, visuf, label, n_global=None):
         """One fwd + bwd + (all-reduce) + Adam step on this rank's shard.  Returns the local loss tensor
         (already scaled by N_rank/N_global; the sum over ranks is the global mean loss)."""
-        self.flat_g.zero_()
+        for p in self.params:
+            p.grad = None                                         # autograd then stores each gradient without an add kernel
         log_prob = self.model(textf, qmask, umask, lengths, acouf, visuf)[0]
         loss = self.loss_fn(log_prob, label)
         n_local = int(sum(lengths))
         if n_global is not None and n_global != n_local:
             loss = loss * (float(n_local) / float(n_global))
         loss.backward()
+        torch._foreach_copy_(self.grad_views, [p.grad for p in self.params])   # one multi-tensor gather into the bucket
         if self.world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
         self.step_count += 1

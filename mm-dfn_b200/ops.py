@@ -154,6 +154,10 @@ GRU_KEYS = [f"{k}_l{l}{sfx}" for l in (0, 1) for sfx in ("", "_reverse")
             for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
 
 
+# placement order of the 16 GRU gradients inside their shared buffer: [ih_l0, ih_l0_rev, hh_l0, hh_l0_rev, biases, l1 ...]
+_GRU_GRAD_ORDER = [0, 4, 1, 5, 2, 3, 6, 7, 8, 12, 9, 13, 10, 11, 14, 15]
+
+
 class BiGRU2Fn(torch.autograd.Function):
     """x (rows,200) [+ rowmap (T,nseq) gather] -> y (T,nseq,200).  16 weights in GRU_KEYS order."""
 
@@ -178,11 +182,18 @@ class BiGRU2Fn(torch.autograd.Function):
         T, nseq, rows = ctx.T, ctx.nseq, x.shape[0]
         dy = _f32c(dy)
         dx = _empty(x.shape, x.device) if ctx.needs_input_grad[0] else None
-        dw = [_empty(t.shape, x.device) for t in w]
+        # all 16 gradients live in ONE zero-filled buffer (a single memset instead of per-GEMM zero-init launches);
+        # weight_ih of the two directions of a layer are adjacent so that one GEMM produces both
+        flat = torch.zeros(sum(t.numel() for t in w), device=x.device, dtype=F32)
+        dw, off = [None] * 16, 0
+        for i in _GRU_GRAD_ORDER:
+            n = w[i].numel()
+            dw[i] = flat[off:off + n].view(w[i].shape)
+            off += n
         wsb = _empty((query("mmdfn_bigru2_bwd_ws_floats", T, nseq, rows),), x.device)
         tab, dtab = ptr_table(w), ptr_table(dw)
         call("mmdfn_bigru2_bwd", T, nseq, rows, ptr(x), ptr(ctx.rowmap, torch.int32), tab, ptr(ctx.mask, U8),
-             ctx.mask_scale, ptr(y), ptr(dy), ptr(ws), ptr(dx), 0, dtab, ptr(wsb), stream())
+             ctx.mask_scale, ptr(y), ptr(dy), ptr(ws), ptr(dx), 0, dtab, 1, ptr(wsb), stream())
         return (dx, None, None, None, None, None, *dw)
 
 
