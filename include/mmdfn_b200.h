@@ -128,13 +128,16 @@ int mmdfn_gcn_stack_fwd(int B, int N, int Lmax, const int* dia_off, const long l
                         const unsigned char* mask_h0, const unsigned char* mask_layers, float mask_scale, float* F,
                         float* ws, void* stream);
 long long mmdfn_gcn_stack_bwd_ws_floats(int n3);
+/* grads_zeroed != 0 (here and in mmdfn_head_bwd): every weight/bias gradient buffer was zero-filled by the caller
+ * (one memset of a shared buffer) and is accumulated into -- no per-GEMM zero-init launches. */
 int mmdfn_gcn_stack_bwd(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* adj_blk,
                         const float* adj_diag, int K, int reason_flag, double lamda, double alpha, const float* W0,
                         const float* const* convW, const float* w_ih, const float* w_hh,
                         const unsigned char* mask_x, const unsigned char* mask_h0, const unsigned char* mask_layers,
                         float mask_scale, const float* F, const float* ws_fwd, const float* dF, float* dX,
                         float* d_adj_blk, float* d_adj_diag, float* dW0, float* db0, float* const* dconvW,
-                        float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, float* ws, void* stream);
+                        float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, int grads_zeroed, float* ws,
+                        void* stream);
 
 /* ---- k9: head + loss (code/model.py:1328-1337 ; code/loss.py:14-34) ---------------------------
  * F (3N,300); mask (N,900) keep bytes or NULL; Wc (C,900); R (3N,300) saved; log_prob (N,C). C <= 16. */
@@ -142,7 +145,7 @@ int mmdfn_head_fwd(int N, int C, const float* F, const unsigned char* mask, floa
                    const float* bc, float* R, float* log_prob, void* stream);
 int mmdfn_head_bwd(int N, int C, const unsigned char* mask, float mask_scale, const float* Wc, const float* R,
                    const float* log_prob, const float* dlog_prob, float* dF, float* dWc, float* dbc,
-                   float* dlogits_ws, void* stream);
+                   int grads_zeroed, float* dlogits_ws, void* stream);
 int mmdfn_focal_loss_fwd(int N, int C, const float* log_prob, const long long* target, const float* alpha,
                          float gamma, int size_average, float* loss, void* stream);
 int mmdfn_focal_loss_bwd(int N, int C, const float* log_prob, const long long* target, const float* alpha,

@@ -163,12 +163,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) adj_spmm_kernel(AdjGeom g, const
 }
 
 // ---------------------------------------------------------------------------------------
-// G = 100 specialisation of the aggregate (the model's graph hidden size).  One CTA (5 warps) = 40 rows x 100 columns
-// of one (dialogue, modality) block; warp w owns rows 8w..8w+7, lane l < 25 columns 4l..4l+3 (8 x 4 register tile, no
-// padded columns).  Operands come in double-buffered K chunks of 32 through cp.async: A rows are read as warp-broadcast 128-bit loads (1 wavefront), the z rows as
-// conflict-free 128-bit loads (4 wavefronts), 128 FFMA per 12 shared loads.  288 CTAs for the 32 x 100 shard = 2 per SM.
+// G = 100 specialisation of the aggregate (the model's graph hidden size).  One CTA = 40 rows x 100 columns of one
+// (dialogue, modality) block: 250 active threads, thread (ty, tx) owns rows 4ty..4ty+3 x columns 4tx..4tx+3, so no
+// lane computes padded columns.  Operands come in K chunks of up to 128 through cp.async (one chunk = the whole
+// block for L <= 128, double-buffered for longer dialogues): A rows are read as warp-broadcast 128-bit loads, the
+// z rows as conflict-free 128-bit loads, 64 FFMA per 8 shared loads.  288 CTAs for the 32 x 100 shard = 2 per SM.
 // ---------------------------------------------------------------------------------------
-constexpr int SP_ROWS = 40, SP_G = 100, SP_KCH = 32, SP_LDA = SP_KCH + 4, SP_THREADS = 160;
+constexpr int SP_ROWS = 40, SP_G = 100, SP_KCH = 128, SP_LDA = SP_KCH + 4;
 constexpr int SP_STAGE_FLOATS = SP_ROWS * SP_LDA + SP_KCH * SP_G;
 constexpr int SP_SMEM = 2 * SP_STAGE_FLOATS * 4;
 
@@ -179,7 +180,7 @@ __device__ __forceinline__ void sp_cp4(float* dst, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(SP_THREADS) adj_spmm100_kernel(AdjGeom g, const float* __restrict__ adj_blk,
+__global__ void __launch_bounds__(256) adj_spmm100_kernel(AdjGeom g, const float* __restrict__ adj_blk,
                                                           const float* __restrict__ adj_diag, const float* __restrict__ x,
                                                           float* __restrict__ y) {
   extern __shared__ __align__(16) float sp_smem[];
@@ -201,37 +202,37 @@ __global__ void __launch_bounds__(SP_THREADS) adj_spmm100_kernel(AdjGeom g, cons
     const int k0 = c * SP_KCH, kc = min(SP_KCH, L - k0), kc4 = (kc + 3) & ~3;
     if (a_vec) {
       const int q = kc >> 2;                                    // L % 4 == 0 -> kc % 4 == 0
-      for (int i = tid; i < nrows * q; i += SP_THREADS) {
+      for (int i = tid; i < nrows * q; i += 256) {
         const int r = i / q, c4 = i - r * q;
         sp_cp16(As + r * SP_LDA + 4 * c4, A + (i64)r * L + k0 + 4 * c4);
       }
     } else {
-      for (int i = tid; i < nrows * kc; i += SP_THREADS) {
+      for (int i = tid; i < nrows * kc; i += 256) {
         const int r = i / kc, k = i - r * kc;
         sp_cp4(As + r * SP_LDA + k, A + (i64)r * L + k0 + k);
       }
-      for (int i = tid; i < nrows * (kc4 - kc); i += SP_THREADS) {      // zero the k tail up to a multiple of 4
+      for (int i = tid; i < nrows * (kc4 - kc); i += 256) {      // zero the k tail up to a multiple of 4
         const int r = i / (kc4 - kc), k = kc + i - r * (kc4 - kc);
         As[r * SP_LDA + k] = 0.f;
       }
     }
-    for (int i = tid; i < (SP_ROWS - nrows) * kc4; i += SP_THREADS) {   // rows beyond the block: zeros
+    for (int i = tid; i < (SP_ROWS - nrows) * kc4; i += 256) {   // rows beyond the block: zeros
       const int r = nrows + i / kc4, k = i % kc4;
       As[r * SP_LDA + k] = 0.f;
     }
     const float* bsrc = Bx + (i64)k0 * SP_G;                     // kc consecutive rows of x are one contiguous run
     if (b_vec) {
-      for (int i = tid; i < kc * (SP_G / 4); i += SP_THREADS) sp_cp16(Bs + 4 * i, bsrc + 4 * i);
+      for (int i = tid; i < kc * (SP_G / 4); i += 256) sp_cp16(Bs + 4 * i, bsrc + 4 * i);
     } else {
-      for (int i = tid; i < kc * SP_G; i += SP_THREADS) sp_cp4(Bs + i, bsrc + i);
+      for (int i = tid; i < kc * SP_G; i += 256) sp_cp4(Bs + i, bsrc + i);
     }
-    for (int i = tid; i < (kc4 - kc) * SP_G; i += SP_THREADS) Bs[kc * SP_G + i] = 0.f;
+    for (int i = tid; i < (kc4 - kc) * SP_G; i += 256) Bs[kc * SP_G + i] = 0.f;
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  const int warp = tid >> 5, tx = tid & 31;
-  const bool active = tx < 25;
-  float acc[8][4];
+  const int tx = tid % 25, ty = tid / 25;                        // ty 0..9 (tid < 250), warps straddle at most 2 row groups
+  const bool active = tid < 250;
+  float acc[4][4];
   zero_acc(acc);
   load_chunk(0, 0);
   for (int c = 0; c < nchunks; c++) {
@@ -244,37 +245,26 @@ __global__ void __launch_bounds__(SP_THREADS) adj_spmm100_kernel(AdjGeom g, cons
     }
     __syncthreads();
     if (active) {
-      const float* As = sp_smem + buf * SP_STAGE_FLOATS + (warp * 8) * SP_LDA;
+      const float* As = sp_smem + buf * SP_STAGE_FLOATS + (ty * 4) * SP_LDA;
       const float* Bs = sp_smem + buf * SP_STAGE_FLOATS + SP_ROWS * SP_LDA + tx * 4;
       const int kc4 = (min(SP_KCH, L - c * SP_KCH) + 3) & ~3;
-      // register double buffering: the fragments of k-quad q+1 are loaded while the 128 FFMAs of k-quad q issue
-      float4 fa[2][8], fb[2][4];
-      auto load_frag = [&](int k, float4 (&a)[8], float4 (&b)[4]) {
+#pragma unroll 2
+      for (int k = 0; k < kc4; k += 4) {
+        float4 a[4], bb[4];
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++) b[kk] = *reinterpret_cast<const float4*>(Bs + (k + kk) * SP_G);
+        for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4*>(As + i * SP_LDA + k);
 #pragma unroll
-        for (int i = 0; i < 8; i++) a[i] = *reinterpret_cast<const float4*>(As + i * SP_LDA + k);
-      };
-      auto fma_frag = [&](const float4 (&a)[8], const float4 (&b)[4]) {
+        for (int kk = 0; kk < 4; kk++) bb[kk] = *reinterpret_cast<const float4*>(Bs + (k + kk) * SP_G);
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < 4; i++) {
           const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
 #pragma unroll
           for (int kk = 0; kk < 4; kk++) {
-            acc[i][0] = fmaf(av[kk], b[kk].x, acc[i][0]);
-            acc[i][1] = fmaf(av[kk], b[kk].y, acc[i][1]);
-            acc[i][2] = fmaf(av[kk], b[kk].z, acc[i][2]);
-            acc[i][3] = fmaf(av[kk], b[kk].w, acc[i][3]);
+            acc[i][0] = fmaf(av[kk], bb[kk].x, acc[i][0]);
+            acc[i][1] = fmaf(av[kk], bb[kk].y, acc[i][1]);
+            acc[i][2] = fmaf(av[kk], bb[kk].z, acc[i][2]);
+            acc[i][3] = fmaf(av[kk], bb[kk].w, acc[i][3]);
           }
-        }
-      };
-      load_frag(0, fa[0], fb[0]);
-      for (int k = 0; k < kc4; k += 8) {
-        if (k + 4 < kc4) load_frag(k + 4, fa[1], fb[1]);
-        fma_frag(fa[0], fb[0]);
-        if (k + 4 < kc4) {
-          if (k + 8 < kc4) load_frag(k + 8, fa[0], fb[0]);
-          fma_frag(fa[1], fb[1]);
         }
       }
     }
@@ -284,8 +274,8 @@ __global__ void __launch_bounds__(SP_THREADS) adj_spmm100_kernel(AdjGeom g, cons
   const int o1 = (m == 0) ? 1 : 0, o2 = (m == 2) ? 1 : 2;
   const int p1 = pair_of(min(m, o1), max(m, o1)), p2 = pair_of(min(m, o2), max(m, o2));
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const int r = row0 + warp * 8 + i;
+  for (int i = 0; i < 4; i++) {
+    const int r = row0 + ty * 4 + i;
     if (r >= L) continue;
     const float d1 = adj_diag[(i64)p1 * g.N + off + r], d2 = adj_diag[(i64)p2 * g.N + off + r];
     const float4 x1 = *reinterpret_cast<const float4*>(x + ((i64)o1 * g.N + off + r) * SP_G + tx * 4);
@@ -309,10 +299,9 @@ int adj_spmm(int B, int N, int Lmax, const int* dia_off, const i64* blk_off, con
       MMDFN_CUDA(cudaFuncSetAttribute(adj_spmm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
       configured = true;
     }
-    // K chunks of 32 are double-buffered (37 KB per CTA): the first FFMAs start after a quarter of a 100-utterance
-    // block has landed, and several CTAs per SM overlap each other's load and compute phases
+    // one operand stage when every block fits a single K chunk (3 CTAs per SM), two (double buffering) otherwise
     const int smem = (Lmax > SP_KCH ? 2 : 1) * SP_STAGE_FLOATS * 4;
-    adj_spmm100_kernel<<<dim3(ceil_div(Lmax, SP_ROWS), 1, B * 3), SP_THREADS, smem, st>>>(g, adj_blk, adj_diag, x, y);
+    adj_spmm100_kernel<<<dim3(ceil_div(Lmax, SP_ROWS), 1, B * 3), 256, smem, st>>>(g, adj_blk, adj_diag, x, y);
     MMDFN_LAUNCH_CHECK();
     return 0;
   }

@@ -216,7 +216,8 @@ extern "C" int mmdfn_gcn_stack_bwd(int B, int N, int Lmax, const int* dia_off, c
                                    const unsigned char* mask_layers, float mask_scale, const float* F,
                                    const float* ws_fwd, const float* dF, float* dX, float* d_adj_blk,
                                    float* d_adj_diag, float* dW0, float* db0, float* const* dconvW, float* dw_ih,
-                                   float* dw_hh, float* db_ih, float* db_hh, float* ws, void* stream) {
+                                   float* dw_hh, float* db_ih, float* db_hh, int grads_zeroed, float* ws,
+                                   void* stream) {
   if (!dia_off || !blk_off || !adj_blk || !adj_diag || !W0 || !F || !ws_fwd || !dF || !dX || !dW0 || !db0 || !ws)
     return MMDFN_ENULL;
   if (K > 0 && (!convW || !dconvW)) return MMDFN_ENULL;
@@ -242,7 +243,8 @@ extern "C" int mmdfn_gcn_stack_bwd(int B, int N, int Lmax, const int* dia_off, c
   copy2d_mask_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3, GG, dF + GX, GF, nullptr, 1.f, dz, GG);
   MMDFN_LAUNCH_CHECK();
   MMDFN_TRY(fill_zero(dh0, (size_t)n3 * GG * sizeof(float), st));
-  if (reason_flag && K == 0) {
+  const float gb = grads_zeroed ? 1.f : 0.f;     // caller pre-zeroed every gradient buffer: accumulate, no zero-init launches
+  if (reason_flag && K == 0 && !grads_zeroed) {
     MMDFN_TRY(fill_zero(dw_ih, 4 * GG * GG * sizeof(float), st));
     MMDFN_TRY(fill_zero(dw_hh, 4 * GG * GG * sizeof(float), st));
     MMDFN_TRY(fill_zero(db_ih, 4 * GG * sizeof(float), st));
@@ -267,8 +269,8 @@ extern "C" int mmdfn_gcn_stack_bwd(int B, int N, int Lmax, const int* dia_off, c
     // dhi += du1 Wtop^T ; dh0 += du1 Wbot^T ; dW = [hi|h0]^T du1
     MMDFN_TRY(gemm(false, true, (int)n3, GG, GG, 1.f, du1, GG, convW[l], GG, 1.f, dhi, GG, nullptr, 0, st));
     MMDFN_TRY(gemm(false, true, (int)n3, GG, GG, 1.f, du1, GG, convW[l] + GG * GG, GG, 1.f, dh0, GG, nullptr, 0, st));
-    MMDFN_TRY(gemm(true, false, GG, GG, (int)n3, 1.f, hi, GG, du1, GG, 0.f, dconvW[l], GG, nullptr, 0, st));
-    MMDFN_TRY(gemm(true, false, GG, GG, (int)n3, 1.f, h0, GG, du1, GG, 0.f, dconvW[l] + GG * GG, GG, nullptr, 0, st));
+    MMDFN_TRY(gemm(true, false, GG, GG, (int)n3, 1.f, hi, GG, du1, GG, gb, dconvW[l], GG, nullptr, 0, st));
+    MMDFN_TRY(gemm(true, false, GG, GG, (int)n3, 1.f, h0, GG, du1, GG, gb, dconvW[l] + GG * GG, GG, nullptr, 0, st));
     const float* agg_in = reason_flag ? h : zprev;
     if (d_adj_blk)
       MMDFN_TRY(adj_grad_accum(B, N, Lmax, dia_off, (const i64*)blk_off, dhi, agg_in, GG, d_adj_blk, d_adj_diag,
@@ -289,22 +291,22 @@ extern "C" int mmdfn_gcn_stack_bwd(int B, int N, int Lmax, const int* dia_off, c
     // dz_l = dz_{l+1} (residual +q) + dgates W_ih ; dhc = dgates W_hh
     MMDFN_TRY(gemm(false, false, (int)n3, GG, 4 * GG, 1.f, dgates, 4 * GG, w_ih, GG, 1.f, dz, GG, nullptr, 0, st));
     if (l > 0) MMDFN_TRY(gemm(false, false, (int)n3, GG, 4 * GG, 1.f, dgates, 4 * GG, w_hh, GG, 0.f, dhc, GG, nullptr, 0, st));
-    const float beta = first_rnn ? 0.f : 1.f;
+    const float beta = (first_rnn && !grads_zeroed) ? 0.f : 1.f;
     MMDFN_TRY(gemm(true, false, 4 * GG, GG, (int)n3, 1.f, dgates, 4 * GG, zprev, GG, beta, dw_ih, GG, nullptr, 0, st));
     MMDFN_TRY(gemm(true, false, 4 * GG, GG, (int)n3, 1.f, dgates, 4 * GG, hprev, GG, beta, dw_hh, GG, nullptr, 0, st));
     MMDFN_TRY(colsum((int)n3, 4 * GG, dgates, 4 * GG, beta, db_ih, st));
     first_rnn = false;
     have_carry = true;
   }
-  if (reason_flag && db_hh) {
+  if (reason_flag && db_hh && K > 0) {
     MMDFN_CUDA(cudaMemcpyAsync(db_hh, db_ih, 4 * GG * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   // through z0 = dropout(h0), h0 = relu(x_d W0^T + b0)
   float* dpre = du1;
   h0_bwd_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3 * GG, dh0, dz, mask_h0, mask_scale, h0, dpre);
   MMDFN_LAUNCH_CHECK();
-  MMDFN_TRY(gemm(true, false, GG, GX, (int)n3, 1.f, dpre, GG, F, GF, 0.f, dW0, GX, nullptr, 0, st));
-  MMDFN_TRY(colsum((int)n3, GG, dpre, GG, 0.f, db0, st));
+  MMDFN_TRY(gemm(true, false, GG, GX, (int)n3, 1.f, dpre, GG, F, GF, gb, dW0, GX, nullptr, 0, st));
+  MMDFN_TRY(colsum((int)n3, GG, dpre, GG, gb, db0, st));
   MMDFN_TRY(gemm(false, false, (int)n3, GX, GG, 1.f, dpre, GG, W0, GX, 0.f, dxd, GX, nullptr, 0, st));
   x_bwd_kernel<<<nblk(n3 * GX), 256, 0, st>>>(n3, dF, dxd, mask_x, mask_scale, dX);
   MMDFN_LAUNCH_CHECK();

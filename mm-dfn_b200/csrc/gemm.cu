@@ -138,8 +138,10 @@ __global__ void colsum_kernel(const float* __restrict__ A, i64 lda, int M, int N
 
 int colsum(int M, int N, const float* A, i64 lda, float beta, float* out, cudaStream_t st) {
   if (N <= 0) return 0;
-  scale2d_kernel<<<ceil_div(N, 256), 256, 0, st>>>(out, N, 1, N, beta);
-  MMDFN_LAUNCH_CHECK();
+  if (beta != 1.f) {
+    scale2d_kernel<<<ceil_div(N, 256), 256, 0, st>>>(out, N, 1, N, beta);
+    MMDFN_LAUNCH_CHECK();
+  }
   if (M <= 0) return 0;
   const int rpb = 256;
   dim3 grid(ceil_div(N, 32), ceil_div(M, rpb));

@@ -146,19 +146,21 @@ extern "C" int mmdfn_head_fwd(int N, int C, const float* F, const unsigned char*
 // dlogits_ws: (N, C) scratch.  dF (3N,300), dWc (C,900), dbc (C) are overwritten.
 extern "C" int mmdfn_head_bwd(int N, int C, const unsigned char* mask, float mask_scale, const float* Wc,
                               const float* R, const float* log_prob, const float* dlog_prob, float* dF, float* dWc,
-                              float* dbc, float* dlogits_ws, void* stream) {
+                              float* dbc, int grads_zeroed, float* dlogits_ws, void* stream) {
   if (!Wc || !R || !log_prob || !dlog_prob || !dF || !dWc || !dbc || !dlogits_ws) return MMDFN_ENULL;
   if (C <= 0 || C > MAXC || N < 0) return MMDFN_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  const float gb = grads_zeroed ? 1.f : 0.f;
   if (N == 0) {
+    if (grads_zeroed) return 0;
     MMDFN_TRY(fill_zero(dWc, (size_t)C * 900 * sizeof(float), st));
     return fill_zero(dbc, (size_t)C * sizeof(float), st);
   }
   log_softmax_bwd_kernel<<<ceil_div(N, 128), 128, 0, st>>>(N, C, log_prob, dlog_prob, dlogits_ws);
   MMDFN_LAUNCH_CHECK();
-  MMDFN_TRY(colsum(N, C, dlogits_ws, C, 0.f, dbc, st));
+  MMDFN_TRY(colsum(N, C, dlogits_ws, C, gb, dbc, st));
   for (int m = 0; m < 3; m++) {
-    MMDFN_TRY(gemm(true, false, C, HF, N, 1.f, dlogits_ws, C, R + (i64)m * N * HF, HF, 0.f, dWc + m * HF, 3 * HF, nullptr, 0, st));
+    MMDFN_TRY(gemm(true, false, C, HF, N, 1.f, dlogits_ws, C, R + (i64)m * N * HF, HF, gb, dWc + m * HF, 3 * HF, nullptr, 0, st));
     MMDFN_TRY(gemm(false, false, N, HF, C, 1.f, dlogits_ws, C, Wc + m * HF, 3 * HF, 0.f, dF + (i64)m * N * HF, HF, nullptr, 0, st));
   }
   head_relu_bwd_kernel<<<(unsigned)ceil_div64((i64)3 * N * HF, 256), 256, 0, st>>>((i64)3 * N * HF, R, mask ? mask_scale : 1.f, dF);

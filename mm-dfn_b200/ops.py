@@ -132,17 +132,21 @@ class Proj3Fn(torch.autograd.Function):
         rows = T * B
         st = stream()
         out = [None] * 9
+        Ks = [x.shape[2] for x in xs]
+        flat = torch.zeros(200 * sum(Ks) + 600, device=dU.device, dtype=F32)      # all six gradients, one memset
+        off = 0
         for m in range(3):
-            K = xs[m].shape[2]
+            K = Ks[m]
             g = dU.data_ptr() + m * rows * 200 * 4
             if ctx.needs_input_grad[m]:
                 dx = _empty(xs[m].shape, dU.device)
                 call("mmdfn_gemm", 0, 0, rows, K, 200, 1.0, g, 200, ptr(ws[m]), K, 0.0, ptr(dx), K, None, 0, st)
                 out[m] = dx
-            dw = _empty((200, K), dU.device)
-            call("mmdfn_gemm", 1, 0, 200, K, rows, 1.0, g, 200, ptr(xs[m]), K, 0.0, ptr(dw), K, None, 0, st)
-            db = _empty((200,), dU.device)
-            call("mmdfn_colsum", rows, 200, g, 200, 0.0, ptr(db), st)
+            dw = flat[off:off + 200 * K].view(200, K)
+            db = flat[off + 200 * K:off + 200 * K + 200]
+            off += 200 * K + 200
+            call("mmdfn_gemm", 1, 0, 200, K, rows, 1.0, g, 200, ptr(xs[m]), K, 1.0, ptr(dw), K, None, 0, st)
+            call("mmdfn_colsum", rows, 200, g, 200, 1.0, ptr(db), st)
             out[3 + 2 * m], out[4 + 2 * m] = dw, db
         return tuple(out)
 
@@ -355,20 +359,23 @@ class GCNStackFn(torch.autograd.Function):
         d_diag = _empty(adj_diag.shape, dev) if want_adj else None
         if want_adj and K == 0:
             d_blk.zero_(); d_diag.zero_()
-        dW0, db0 = _empty(W0.shape, dev), _empty((100,), dev)
-        dw_ih, dw_hh = _empty((400, 100), dev), _empty((400, 100), dev)
-        db_ih, db_hh = _empty((400,), dev), _empty((400,), dev)
-        if not reason_flag:
-            for t in (dw_ih, dw_hh, db_ih, db_hh):
-                t.zero_()
-        dconv = [_empty((200, 100), dev) for _ in range(K)]
+        # every parameter gradient of the stack lives in ONE zero-filled buffer (a single memset)
+        sizes = [20000, 100, 40000, 40000, 400, 400] + [20000] * K
+        flat = torch.zeros(sum(sizes), device=dev, dtype=F32)
+        views, off = [], 0
+        for n in sizes:
+            views.append(flat[off:off + n])
+            off += n
+        dW0, db0 = views[0].view(100, 200), views[1]
+        dw_ih, dw_hh, db_ih, db_hh = views[2].view(400, 100), views[3].view(400, 100), views[4], views[5]
+        dconv = [v.view(200, 100) for v in views[6:]]
         wsb = _empty((query("mmdfn_gcn_stack_bwd_ws_floats", n3),), dev)
         tab = ptr_table(convW) if K > 0 else None
         dtab = ptr_table(dconv) if K > 0 else None
         call("mmdfn_gcn_stack_bwd", *geom.args(), ptr(adj_blk), ptr(adj_diag), K, reason_flag, lamda, alpha, ptr(W0),
              tab, ptr(w_ih), ptr(w_hh), ptr(mask_x, U8), ptr(mask_h0, U8), ptr(mask_layers, U8), mask_scale,
              ptr(F_), ptr(ws), ptr(dF), ptr(dX), ptr(d_blk), ptr(d_diag), ptr(dW0), ptr(db0), dtab, ptr(dw_ih),
-             ptr(dw_hh), ptr(db_ih), ptr(db_hh), ptr(wsb), stream())
+             ptr(dw_hh), ptr(db_ih), ptr(db_hh), 1, ptr(wsb), stream())
         return (dX, d_blk, d_diag, None, None, None, None, None, None, None, None, None,
                 dW0, db0, dw_ih, dw_hh, db_ih, db_hh, *dconv)
 
@@ -396,10 +403,12 @@ class HeadFn(torch.autograd.Function):
         N, C = ctx.N, Wc.shape[0]
         dev = R.device
         dlp = _f32c(dlp)
-        dF, dWc, dbc = _empty(R.shape, dev), _empty(Wc.shape, dev), _empty((C,), dev)
+        dF = _empty(R.shape, dev)
+        flat = torch.zeros(C * 900 + C, device=dev, dtype=F32)
+        dWc, dbc = flat[:C * 900].view(C, 900), flat[C * 900:]
         scratch = _empty((max(N, 1), C), dev)
         call("mmdfn_head_bwd", N, C, ptr(ctx.mask, U8), ctx.mask_scale, ptr(Wc), ptr(R), ptr(lp), ptr(dlp), ptr(dF),
-             ptr(dWc), ptr(dbc), ptr(scratch), stream())
+             ptr(dWc), ptr(dbc), 1, ptr(scratch), stream())
         return dF, None, None, None, dWc, dbc
 
 

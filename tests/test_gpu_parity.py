@@ -265,6 +265,28 @@ def test_spmm_and_grad(lengths, G):
     assert maxerr(dg.grad, exp_dg) < 1e-4
 
 
+def test_long_dialogues_chunked_paths():
+    """L > 128 (BASELINE config 5 has 500-utterance dialogues): the aggregate's multi-chunk K loop, the adjacency
+    kernels' multi-tile grids and their backward, against the oracle."""
+    mm, ops, L = _mods()
+    lengths = [300, 131]
+    N = sum(lengths)
+    feats = [rnd(N, 200, seed=s) for s in (1, 2, 3)]
+    fc = [f.clone().requires_grad_(True) for f in feats]
+    blocks, diags = O.adj_blocks(fc, lengths, 1.0)
+    x = rnd(3 * N, 100, seed=7)
+    gy = rnd(3 * N, 100, seed=8)
+    y_ref = O.adj_matmul_blocks(blocks, diags, lengths, x)
+    (y_ref * gy).sum().backward()
+    geom = ops.DialogGeom(lengths, DEV)
+    X = torch.cat(feats, 0).to(DEV).requires_grad_(True)
+    blk, dg = ops.AdjFn.apply(X, geom, 1.0)
+    y = ops.SpmmFn.apply(blk, dg, x.to(DEV), geom)
+    assert maxerr(y, y_ref) < 2e-5
+    (y * gy.to(DEV)).sum().backward()
+    assert relerr(X.grad, torch.cat([f.grad for f in fc], 0)) < 2e-3
+
+
 def test_spmm_degree_identity_large():
     """size-independent property at BASELINE sizes: A_hat (D^1/2 1) = D^1/2 1 (rows of D^-1/2 S D^-1/2)."""
     mm, ops, L = _mods()
