@@ -120,7 +120,7 @@ def cpu_reference_steps(steps, warmup, n_dialogues=CPU_SAMPLE_DIALOGUES, max_sec
                       f"fwd+bwd+Adam, dropout {DROPOUT}, mean of {len(times)} steps"}
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -131,7 +131,7 @@ def run_reference_arm(args):
             "config": workload_config(args.gpus), "gpu_launches": 0,
             "cpu_baseline": {"value": r["utt_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["utt_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -222,7 +222,19 @@ def roofline_graph_conv(dev, n_dialogues=DIALOGUES_PER_GPU):
             "note": "launch covers one GCN layer of the %dx100 shard; operands rotated over %d copies (> L2)" % (n_dialogues, copies)}
 
 
+def _claim_stdout():
+    """The driver reads ONE JSON line from stdout, but libraries (NCCL's version banner, the reference-style
+    'construct GDF' print) also write there.  Point fd 1 at stderr for the whole run and keep the real stdout
+    for the final line only."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w")
+    return real
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -231,7 +243,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, real_stdout)
 
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -353,7 +365,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_steps(steps=3, warmup=1, max_seconds=60.0)
             line["cpu_baseline"] = {"value": r["utt_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

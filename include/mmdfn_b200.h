@@ -171,6 +171,26 @@ int mmdfn_edge_attn_bwd(int T, int B, int Lmax, int ncol, int window_past, int w
 int mmdfn_edge_scores_dense(long long E, int B, int msl, int T, const long long* edge_index, const int* node_dia,
                             const int* dia_off, float* edge_norm, float* dense, int gather, void* stream);
 
+/* ---- k12 (relation graph type): RGCNConv -> GraphConv of GraphNetwork (code/model.py:675-715; arithmetic of
+ * torch-geometric 1.4.3, restated -- parity unpinned).  Windowed edges make every node's in- and out-edges contiguous
+ * ranges, so aggregation is a warp-per-node gather-reduce without atomics.  node_spk (N) int32 = speaker of each node
+ * (first p with qmask == 1).  xw (N, R, G) = x W_r for all relations (one mmdfn_gemm); norm (E) edge weights. */
+int mmdfn_node_speakers(int B, int S, const int* dia_off, const float* qmask, int* node_spk, void* stream);
+/* out[i,:] += sum_{j->i} norm[e] * xw[j, type(e), :] */
+int mmdfn_rgcn_aggregate_fwd(int N, int G, int R, int S, int window_past, int window_future, const int* dia_off,
+                             const int* node_dia, const int* node_spk, const long long* row_ptr, const float* xw,
+                             const float* norm, float* out, void* stream);
+/* dxw (N,R,G) "=" (zero-filled here), dnorm (E) "=" */
+int mmdfn_rgcn_aggregate_bwd(int N, int G, int R, int S, int window_past, int window_future, const int* dia_off,
+                             const int* node_dia, const int* node_spk, const long long* row_ptr, const float* xw,
+                             const float* norm, const float* dout, float* dxw, float* dnorm, void* stream);
+/* out[i,:] (+)= sum of h[j,:] over j in [i-reach_back, i+reach_fwd] inside i's dialogue (-1 = unbounded):
+ * GraphConv forward uses (window_future, window_past), its backward (window_past, window_future). */
+int mmdfn_window_sum(int N, int G, int reach_back, int reach_fwd, const int* dia_off, const int* node_dia,
+                     const float* h, float* out, int accumulate, void* stream);
+/* out[b][c][r] = in[b][r][c] */
+int mmdfn_transpose_batched(int batch, int rows, int cols, const float* in, float* out, void* stream);
+
 /* ---- support: dropout keep masks, fused flat-buffer Adam(+L2) (code/run_train_erc.py:512) ----- */
 int mmdfn_dropout_mask(long long n, float p, unsigned long long seed, unsigned long long offset,
                        unsigned char* mask, void* stream);

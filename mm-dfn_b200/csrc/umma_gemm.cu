@@ -256,9 +256,11 @@ __global__ void __launch_bounds__(UG_ALL_THREADS, 2) umma_gemm_kernel(UGemmArgs 
   uint32_t free_parity = 1;             // parity to wait for on bar_free[s]; flips every time s wraps (first use: no wait)
   for (int c = 0; c < nchunks; c++) {
     const bool is_last = (c == nchunks - 1);
+    UG_STAMP();                                           // [0] loop top
     stage_chunk(c + UG_DEPTH - 1);
+    UG_STAMP();                                           // [1] cp.async issued
     cp_async_wait<UG_DEPTH - 1>();                        // this thread's pieces of chunk c have landed
-    UG_STAMP();
+    UG_STAMP();                                           // [2] landed
     const uint8_t* raw = raw_ptr + ring_r * UG_RAW_STAGE;
     float4 va[2], vb[2];
 #pragma unroll
@@ -267,16 +269,17 @@ __global__ void __launch_bounds__(UG_ALL_THREADS, 2) umma_gemm_kernel(UGemmArgs 
       vb[i] = b_vec ? *reinterpret_cast<const float4*>(raw + ob.raw_off[i]) : ob.read_scalar(i, is_last);
     }
     if (c >= UG_STAGES) umma::mbar_wait(&bar_free[s], free_parity);   // MMAs of chunk c-2 released stage s
-    UG_STAMP();
+    UG_STAMP();                                           // [3] stage free
     uint8_t* st = smem + s * UG_STAGE_BYTES;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
       oa.convert(i, va[i], st, st + UG_A_PART);
       ob.convert(i, vb[i], st + 2 * UG_A_PART, st + 2 * UG_A_PART + UG_B_PART);
     }
+    UG_STAMP();                                           // [4] converted + stored
     umma::fence_proxy_async_smem();                       // my generic-proxy writes -> visible to the tensor core
+    UG_STAMP();                                           // [5] fenced
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(&bar_full[s])) : "memory");
-    UG_STAMP();
     ring_r = (ring_r + 1 == UG_DEPTH) ? 0 : ring_r + 1;
     if (++s == UG_STAGES) { s = 0; free_parity ^= 1; }
   }

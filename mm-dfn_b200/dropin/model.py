@@ -2,7 +2,7 @@
 import _bootstrap  # noqa: F401
 from mmdfn_b200.modules import (Attention, DialogueGNNModel, MaskedEdgeAttention, MatchingAttention,  # noqa: F401
                                 MMGatedAttention, SimpleAttention, simple_batch_graphify)
-from mmdfn_b200.relation import batch_graphify, edge_perms  # noqa: F401
+from mmdfn_b200.relation import GraphNetwork, batch_graphify, edge_perms  # noqa: F401
 
 
 def _outside_hot_path(name):

@@ -38,6 +38,7 @@ class EdgeSet:
         T, B, S = qmask.shape
         dev = qmask.device
         self.geom, self.wp, self.wf = geom, int(window_past), int(window_future)
+        self.node_spk, self.S = None, S
         self.counts = [edge_count(L, self.wp, self.wf) for L in geom.lengths]
         off = np.concatenate([[0], np.cumsum(self.counts)]).astype(np.int64)
         self.E = int(off[-1])
@@ -149,6 +150,194 @@ def batch_graphify(features, qmask, lengths, window_past, window_future, edge_ty
     from .modules import _geom_of
     geom = _geom_of(lengths, features.device)
     edges = EdgeSet(qmask, geom, window_past, window_future)
+    _node_speakers(edges, qmask)
     edge_norm = EdgeAttnFn.apply(features, att_model.scalar.weight, edges)
     node_features = torch.cat([features[:lengths[j], j, :] for j in range(features.size(1))], dim=0)
+    edges.edge_index._mmdfn_edges = edges          # lets RGCNConv / GraphConv recover the windowed structure
     return node_features, edges.edge_index, edge_norm, edges.edge_type, list(edges.counts)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# a12: GraphNetwork = RGCNConv -> GraphConv (code/model.py:675-715).  The two layers are torch-geometric 1.4.3
+# modules in the reference (not vendored / not installed): parameter names, shapes and forward semantics below
+# follow PyG 1.4.3 (RGCNConv: basis, att, root, bias; GraphConv: weight, lin.{weight,bias}) -- parity unpinned.
+# ------------------------------------------------------------------------------------------------------------
+def _gemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, beta=0.0, bias=None):
+    call("mmdfn_gemm", int(ta), int(tb), M, N, K, 1.0, A, lda, B, ldb, float(beta), C, ldc, bias, 0, stream())
+
+
+def _node_speakers(edges, qmask):
+    if getattr(edges, "node_spk", None) is None:
+        q = ops._f32c(qmask)
+        T, B, S = q.shape
+        edges.node_spk = torch.empty((max(edges.geom.N, 1),), dtype=I32, device=q.device)
+        edges.S = S
+        call("mmdfn_node_speakers", B, S, ptr(edges.geom.dia_off, I32), ptr(q), ptr(edges.node_spk, I32), stream())
+    return edges.node_spk
+
+
+class RGCNConvFn(torch.autograd.Function):
+    """out_i = sum_{j->i} norm_e (x_j W_{type_e}) + x_i root + bias,  W_r = sum_b att[r,b] basis[b]."""
+
+    @staticmethod
+    def forward(ctx, x, edge_norm, basis, att, root, bias, edges):
+        x, edge_norm, basis, att, root, bias = (ops._f32c(t) for t in (x, edge_norm, basis, att, root, bias))
+        geom = edges.geom
+        N, fin = x.shape
+        nb, _, fout = basis.shape
+        R = att.shape[0]
+        dev = x.device
+        basisT = torch.empty((nb, fout, fin), device=dev)
+        call("mmdfn_transpose_batched", nb, fin, fout, ptr(basis), ptr(basisT), stream())
+        Wt = torch.empty((R, fout * fin), device=dev)                   # Wt[r, o, i] = W_r[i, o]
+        _gemm(0, 0, R, fout * fin, nb, ptr(att), nb, ptr(basisT), fout * fin, ptr(Wt), fout * fin)
+        xw = torch.empty((N, R * fout), device=dev)                     # xw[n, r, o] = (x W_r)[n, o]
+        _gemm(0, 1, N, R * fout, fin, ptr(x), fin, ptr(Wt), fin, ptr(xw), R * fout)
+        out = torch.empty((N, fout), device=dev)
+        _gemm(0, 0, N, fout, fin, ptr(x), fin, ptr(root), fout, ptr(out), fout, bias=ptr(bias))
+        call("mmdfn_rgcn_aggregate_fwd", N, fout, R, edges.S, edges.wp, edges.wf, ptr(geom.dia_off, I32),
+             ptr(edges.node_dia, I32), ptr(edges.node_spk, I32), ptr(edges.row_ptr, I64), ptr(xw), ptr(edge_norm), ptr(out),
+             stream())
+        ctx.save_for_backward(x, edge_norm, basisT, att, root, Wt, xw)
+        ctx.edges = edges
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, edge_norm, basisT, att, root, Wt, xw = ctx.saved_tensors
+        edges, geom = ctx.edges, ctx.edges.geom
+        dout = ops._f32c(dout)
+        N, fin = x.shape
+        nb, fout, _ = basisT.shape
+        R = att.shape[0]
+        dev = x.device
+        dxw = torch.empty_like(xw)
+        dnorm = torch.empty_like(edge_norm)
+        call("mmdfn_rgcn_aggregate_bwd", N, fout, R, edges.S, edges.wp, edges.wf, ptr(geom.dia_off, I32),
+             ptr(edges.node_dia, I32), ptr(edges.node_spk, I32), ptr(edges.row_ptr, I64), ptr(xw), ptr(edge_norm), ptr(dout),
+             ptr(dxw), ptr(dnorm), stream())
+        d_root = torch.empty_like(root)
+        _gemm(1, 0, fin, fout, N, ptr(x), fin, ptr(dout), fout, ptr(d_root), fout)
+        d_bias = torch.empty((fout,), device=dev)
+        call("mmdfn_colsum", N, fout, ptr(dout), fout, 0.0, ptr(d_bias), stream())
+        dx = torch.empty_like(x)
+        _gemm(0, 1, N, fin, fout, ptr(dout), fout, ptr(root), fout, ptr(dx), fin)                  # dout root^T
+        _gemm(0, 0, N, fin, R * fout, ptr(dxw), R * fout, ptr(Wt), fin, ptr(dx), fin, beta=1.0)    # + dxw Wt
+        dWt = torch.empty_like(Wt)
+        _gemm(1, 0, R * fout, fin, N, ptr(dxw), R * fout, ptr(x), fin, ptr(dWt), fin)
+        d_att = torch.empty_like(att)
+        _gemm(0, 1, R, nb, fout * fin, ptr(dWt), fout * fin, ptr(basisT), fout * fin, ptr(d_att), nb)
+        d_basisT = torch.empty_like(basisT)
+        _gemm(1, 0, nb, fout * fin, R, ptr(att), nb, ptr(dWt), fout * fin, ptr(d_basisT), fout * fin)
+        d_basis = torch.empty((nb, fin, fout), device=dev)
+        call("mmdfn_transpose_batched", nb, fout, fin, ptr(d_basisT), ptr(d_basis), stream())
+        return dx, dnorm, d_basis, d_att, d_root, d_bias, None
+
+
+class GraphConvFn(torch.autograd.Function):
+    """out_i = sum_{j->i} (x W)_j + Linear(x_i)   (aggr='add', no edge weights)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, lin_w, lin_b, edges):
+        x, weight, lin_w, lin_b = (ops._f32c(t) for t in (x, weight, lin_w, lin_b))
+        geom = edges.geom
+        N, fin = x.shape
+        fout = weight.shape[1]
+        dev = x.device
+        h = torch.empty((N, fout), device=dev)
+        _gemm(0, 0, N, fout, fin, ptr(x), fin, ptr(weight), fout, ptr(h), fout)
+        out = torch.empty((N, fout), device=dev)
+        _gemm(0, 1, N, fout, fin, ptr(x), fin, ptr(lin_w), fin, ptr(out), fout, bias=ptr(lin_b))
+        call("mmdfn_window_sum", N, fout, edges.wf, edges.wp, ptr(geom.dia_off, I32), ptr(edges.node_dia, I32), ptr(h),
+             ptr(out), 1, stream())
+        ctx.save_for_backward(x, weight, lin_w)
+        ctx.edges = edges
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, lin_w = ctx.saved_tensors
+        edges, geom = ctx.edges, ctx.edges.geom
+        dout = ops._f32c(dout)
+        N, fin = x.shape
+        fout = weight.shape[1]
+        dev = x.device
+        dh = torch.empty((N, fout), device=dev)
+        call("mmdfn_window_sum", N, fout, edges.wp, edges.wf, ptr(geom.dia_off, I32), ptr(edges.node_dia, I32), ptr(dout),
+             ptr(dh), 0, stream())
+        d_weight = torch.empty_like(weight)
+        _gemm(1, 0, fin, fout, N, ptr(x), fin, ptr(dh), fout, ptr(d_weight), fout)
+        dx = torch.empty_like(x)
+        _gemm(0, 1, N, fin, fout, ptr(dh), fout, ptr(weight), fout, ptr(dx), fin)                 # dh W^T
+        _gemm(0, 0, N, fin, fout, ptr(dout), fout, ptr(lin_w), fin, ptr(dx), fin, beta=1.0)       # + dout lin_w
+        d_lin_w = torch.empty_like(lin_w)
+        _gemm(1, 0, fout, fin, N, ptr(dout), fout, ptr(x), fin, ptr(d_lin_w), fin)
+        d_lin_b = torch.empty((fout,), device=dev)
+        call("mmdfn_colsum", N, fout, ptr(dout), fout, 0.0, ptr(d_lin_b), stream())
+        return dx, d_weight, d_lin_w, d_lin_b, None
+
+
+def _edges_of(edge_index):
+    edges = getattr(edge_index, "_mmdfn_edges", None)
+    if edges is None:
+        raise NotImplementedError("edge tensors must come from mmdfn_b200.relation.batch_graphify (windowed edge sets)")
+    return edges
+
+
+class RGCNConv(torch.nn.Module):
+    """torch_geometric.nn.RGCNConv(in, out, num_relations, num_bases) of PyG 1.4.3 (same parameter names / shapes)."""
+
+    def __init__(self, in_channels, out_channels, num_relations, num_bases, root_weight=True, bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_relations, self.num_bases = num_relations, num_bases
+        self.basis = torch.nn.Parameter(torch.Tensor(num_bases, in_channels, out_channels))
+        self.att = torch.nn.Parameter(torch.Tensor(num_relations, num_bases))
+        self.root = torch.nn.Parameter(torch.Tensor(in_channels, out_channels))
+        self.bias = torch.nn.Parameter(torch.Tensor(out_channels))
+        bound = 1.0 / (num_bases * in_channels) ** 0.5            # PyG: uniform(num_bases * in_channels, tensor)
+        for p in (self.basis, self.att, self.root, self.bias):
+            p.data.uniform_(-bound, bound)
+
+    def forward(self, x, edge_index, edge_type, edge_norm=None, size=None):
+        edges = _edges_of(edge_index)
+        if edge_norm is None:
+            edge_norm = torch.ones((edges.E,), device=x.device)
+        return RGCNConvFn.apply(x, edge_norm, self.basis, self.att, self.root, self.bias, edges)
+
+
+class GraphConv(torch.nn.Module):
+    """torch_geometric.nn.GraphConv(in, out, aggr='add') of PyG 1.4.3."""
+
+    def __init__(self, in_channels, out_channels, aggr='add', bias=True):
+        super().__init__()
+        if aggr != 'add':
+            raise NotImplementedError("only aggr='add'")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = torch.nn.Parameter(torch.Tensor(in_channels, out_channels))
+        self.lin = torch.nn.Linear(in_channels, out_channels, bias=bias)
+        bound = 1.0 / in_channels ** 0.5
+        self.weight.data.uniform_(-bound, bound)
+
+    def forward(self, x, edge_index, edge_weight=None, size=None):
+        if edge_weight is not None:
+            raise NotImplementedError("GraphNetwork calls conv2 without edge weights (code/model.py:709)")
+        return GraphConvFn.apply(x, self.weight, self.lin.weight, self.lin.bias, _edges_of(edge_index))
+
+
+class GraphNetwork(torch.nn.Module):
+    """code/model.py:675-715 with return_feature=True (the multi-modal relation configuration): cat([x, conv2(conv1(x))])."""
+
+    def __init__(self, num_features, num_classes, num_relations, max_seq_len, hidden_size=64, dropout=0.5, no_cuda=False,
+                 use_GCN=False, return_feature=False):
+        super().__init__()
+        if use_GCN or not return_feature:
+            raise NotImplementedError("only use_GCN=False, return_feature=True (nodal-attention head is out of scope)")
+        self.return_feature, self.no_cuda, self.use_GCN = return_feature, no_cuda, use_GCN
+        self.conv1 = RGCNConv(num_features, hidden_size, num_relations, num_bases=30)
+        self.conv2 = GraphConv(hidden_size, hidden_size)
+
+    def forward(self, x, edge_index, edge_norm, edge_type, seq_lengths, umask, nodal_attn, avec):
+        out = self.conv1(x, edge_index, edge_type, edge_norm)
+        out = self.conv2(out, edge_index)
+        return torch.cat([x, out], dim=-1)

@@ -87,3 +87,47 @@ def test_masked_edge_attention_module_api():
     ref = O.masked_edge_attention(M, att.scalar.weight.detach().cpu(), lengths, 10, 10)
     assert sc.shape == (B, 200, T)
     assert float((sc.cpu() - ref).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("lengths,S,wp,wf", [([37, 12, 50], 2, 10, 10), ([5, 1, 23], 9, 3, 7), ([30, 8], 3, -1, 4)])
+def test_graph_network_rgcn_graphconv_vs_oracle(lengths, S, wp, wf):
+    """a12: RGCNConv -> GraphConv (PyG 1.4.3 semantics as restated in the oracle; parity unpinned by the reference)."""
+    mm, ops, rel = _mods()
+    rs = np.random.RandomState(5 + S)
+    T, B, N = max(lengths), len(lengths), sum(lengths)
+    q = np.zeros((T, B, S), np.float32)
+    spk = rs.randint(0, S, size=(T, B))
+    for b, L in enumerate(lengths):
+        q[np.arange(L), b, spk[:L, b]] = 1
+    feats = torch.from_numpy(rs.standard_normal((T, B, 200)).astype(np.float32))
+    att = mm.MaskedEdgeAttention(200, 200, False)
+    att.load_state_dict(O.formula_weights({k: tuple(t.shape) for k, t in att.state_dict().items()}, seed=9))
+    R = 2 * S * S
+    net = rel.GraphNetwork(200, 6, R, 200, 100, 0.4, False, False, True)
+    net.load_state_dict(O.formula_weights({k: tuple(t.shape) for k, t in net.state_dict().items()}, seed=13))
+    P = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    Wc = att.scalar.weight.detach().clone().requires_grad_(True)
+    # oracle
+    fc = feats.clone().requires_grad_(True)
+    ei, et, counts = O.build_edges(q, lengths, wp, wf)
+    en = O.edge_norms(O.masked_edge_attention(fc, Wc, lengths, wp, wf), lengths, wp, wf)
+    x = O.ragged_pack(fc, lengths)
+    h1 = O.rgcn_conv(x, ei, et, en, P["conv1.basis"], P["conv1.att"], P["conv1.root"], P["conv1.bias"])
+    h2 = O.pyg_graph_conv(h1, ei, P["conv2.weight"], P["conv2.lin.weight"], P["conv2.lin.bias"])
+    out_ref = torch.cat([x, h2], -1)
+    g = torch.from_numpy(rs.standard_normal(out_ref.shape).astype(np.float32))
+    (out_ref * g).sum().backward()
+    # kernels
+    net, att = net.to(DEV), att.to(DEV)
+    fg = feats.to(DEV).requires_grad_(True)
+    nf, edge_index, edge_norm, edge_type, eil = rel.batch_graphify(fg, torch.from_numpy(q).to(DEV), lengths, wp, wf, {}, att, False)
+    out = net(nf, edge_index, edge_norm, edge_type, lengths, None, False, False)
+    assert out.shape == (N, 300)
+    err = float((out.detach().cpu() - out_ref.detach()).abs().max())
+    assert err < 2e-5, err
+    (out * g.to(DEV)).sum().backward()
+    rel_err = lambda a, b: float((a.cpu() - b).norm() / max(float(b.norm()), 1e-8))
+    assert rel_err(fg.grad, fc.grad) < 2e-4
+    assert rel_err(att.scalar.weight.grad, Wc.grad) < 2e-4
+    for k, p in net.named_parameters():
+        assert rel_err(p.grad, P[k].grad) < 2e-4, k

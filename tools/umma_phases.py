@@ -18,10 +18,12 @@ def run(ta,tb,M,N,K):
     st = [x - t0 for x in d[:n]]
     print(f"--- ta={ta} tb={tb} M={M} N={N} K={K}: {n} stamps; prologue={st[1]}")
     i = 2; c = 0
-    while i + 2 < n - 3:
-        w, fr, ar = st[i], st[i+1], st[i+2]
-        print(f"  chunk {c:2d}: landed@{w:7d} lds+wait_free+={fr-w:5d} convert+fence+arrive+={ar-fr:5d}")
-        i += 3; c += 1
+    while i + 5 < n - 3:
+        a = st[i:i+6]
+        nxt = st[i+6] if i + 6 < n - 3 else a[5]
+        print(f"  chunk {c:2d}: top@{a[0]:7d} issue_cpasync={a[1]-a[0]:5d} wait_group={a[2]-a[1]:5d} lds+stage_free={a[3]-a[2]:5d} "
+              f"split+sts={a[4]-a[3]:5d} fence={a[5]-a[4]:5d} arrive+loop={nxt-a[5]:5d}")
+        i += 6; c += 1
     print(f"  mma_done@{st[n-3]}  epilogue+={st[n-2]-st[n-3]}  dealloc+={st[n-1]-st[n-2]} total={st[n-1]}")
 run(0,1,38400,300,200)
 run(1,0,300,200,19200)
