@@ -20,7 +20,9 @@ namespace mmdfn {
 
 constexpr int UG_THREADS = 256;       // converter / epilogue threads (warps 0-7)
 constexpr int UG_ALL_THREADS = UG_THREADS + 32;   // + warp 8: the MMA issuer
-constexpr int UG_BN = 112;         // output columns per CTA (N = 100 / 200 / 300 / 400 / 600 -> 1 / 2 / 3 / 4 / 6 tiles)
+// output columns per CTA: 112 (two CTAs per SM), 160 or 224 (one CTA per SM).  The wider tiles amortise the A operand's
+// shared-memory traffic (staging in/out, hi+lo stores, tensor-core reads) over more columns: at 112 columns a 16-wide K
+// chunk moves ~870 smem wavefronts for 675 cycles of MMA (smem-bound), at 224 ~1220 for 1344 cycles (tensor-bound).
 constexpr int UG_KC = 16;          // K elements per stage (2 k-steps of 8)
 constexpr int UG_STAGES = 2;       // UMMA operand stages (hi/lo split tiles)
 // K-major operand stage (source rows K-contiguous): core matrix = 8 rows x 16 B; the 4 core matrices of a row group
@@ -29,19 +31,20 @@ constexpr int UG_LBO = 128;        // bytes between the two core matrices of one
 constexpr int UG_SBO = 528;        // bytes between 8-row groups
 // MN-contiguous sources are transposed on the way into the same K-major layout (the tf32 MMA returned zeros with the
 // MN-major descriptor bit in the SWIZZLE_NONE layout on this part -- tools/umma_probe.py -- so one layout serves all).
-constexpr int UG_TMEM_COLS = 256;  // [0,112): hi*hi accumulator, [128,240): correction accumulator
-constexpr int UG_CORR_COL = 128;
-constexpr int UG_RAW_STAGE = UG_THREADS * 4 * 16;   // 4 x 16 B per thread per chunk (2 A + 2 B pieces)
-
-// shared-memory budget per GEMM form, sized so that two CTAs fit one SM (<= ~113 KB each)
-template <int MODE>
+// per-(form, tile width) budget: shared memory, TMEM columns, pieces per converter thread
+template <int MODE, int BN>
 struct UGLayout {
   static constexpr bool A_KMAJ = (MODE != 2), B_KMAJ = (MODE == 0);
+  // 16-byte B pieces per thread per chunk: K-contiguous source 2 / 3 / 4; MN-contiguous source 2 per 128-row pass
+  static constexpr int NPB = B_KMAJ ? (BN * 4 + UG_THREADS - 1) / UG_THREADS : 2 * ((BN + 127) / 128);
   static constexpr int A_PART = 16 * UG_SBO;                 // 8448: both operands live in the K-major layout
-  static constexpr int B_PART = (UG_BN / 8) * UG_SBO;        // 7392
+  static constexpr int B_PART = (BN / 8) * UG_SBO;
   static constexpr int STAGE_BYTES = 2 * (A_PART + B_PART);
   static constexpr int DEPTH = 3;                            // cp.async ring depth
-  static constexpr int SMEM = UG_STAGES * STAGE_BYTES + DEPTH * UG_RAW_STAGE;                  // 110 KB
+  static constexpr int RAW_STAGE = UG_THREADS * (2 + NPB) * 16;
+  static constexpr int SMEM = UG_STAGES * STAGE_BYTES + DEPTH * RAW_STAGE;     // 110 KB (BN=112) ... 160 KB (BN=224)
+  static constexpr int CORR_COL = BN <= 128 ? 128 : 256;     // hi*hi accumulator at column 0, corrections here
+  static constexpr int TMEM_COLS = BN <= 128 ? 256 : 512;
 };
 
 struct UGemmArgs {
@@ -70,19 +73,20 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   !KMAJ (MN-contiguous,     element (r,k) at g[k*ld+r]):  piece i = k (warp + 8 i),         rows 4*lane .. 4*lane+3
 template <int R, bool KMAJ>
 struct OperandThread {
-  const char* ptr[2];     // source address of the piece for the next chunk to stage (always a readable address)
-  i64 stride[2];          // bytes between consecutive K chunks (0 for pieces outside the matrix)
-  int full[2], tail[2];   // valid bytes in a full chunk / in the last chunk
-  uint32_t raw_off[2];    // staging slot offset inside a ring stage
-  int st_off[2];          // destination offset inside an operand part (-1: this thread has no such piece)
-  int kofs[2];
+  static constexpr int NP = KMAJ ? (R * 4 + UG_THREADS - 1) / UG_THREADS : 2 * ((R + 127) / 128);    // pieces per thread per chunk
+  const char* ptr[NP];    // source address of the piece for the next chunk to stage (always a readable address)
+  i64 stride[NP];         // bytes between consecutive K chunks (0 for pieces outside the matrix)
+  int full[NP], tail[NP]; // valid bytes in a full chunk / in the last chunk
+  uint32_t raw_off[NP];   // staging slot offset inside a ring stage
+  int st_off[NP];         // destination offset inside an operand part (-1: this thread has no such piece)
+  int kofs[NP];
 
   __device__ __forceinline__ void init(const float* g, i64 ld, int row0, int row_end, int kb, int ke, int nchunks,
                                        int slot_base) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k_last = kb + (nchunks - 1) * UG_KC;
 #pragma unroll
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NP; i++) {
       raw_off[i] = (uint32_t)(((slot_base + i) * UG_THREADS + threadIdx.x) * 16);
       bool ok;
       if (KMAJ) {
@@ -96,7 +100,8 @@ struct OperandThread {
         full[i] = ok ? 16 : 0;
         tail[i] = ok ? max(0, min(16, 4 * (ke - (k_last + 4 * c)))) : 0;
       } else {
-        const int kl = warp + 8 * i, r = 4 * lane;
+        // piece i: k = warp + 8*(i & 1), rows 128*(i >> 1) + 4*lane .. +3
+        const int kl = warp + 8 * (i & 1), r = 128 * (i >> 1) + 4 * lane;
         const int row = row0 + r;
         kofs[i] = kl;
         st_off[i] = (r < R) ? ((r >> 3) * UG_SBO + (r & 7) * 16 + (kl >> 2) * UG_LBO + (kl & 3) * 4) : -1;
@@ -112,7 +117,7 @@ struct OperandThread {
   // asynchronous copy of the next chunk into the staging ring
   __device__ __forceinline__ void stage(bool is_last, uint32_t raw_base) {
 #pragma unroll
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NP; i++) {
       if (st_off[i] < 0) continue;                    // compile-time for R = 128, warp-uniform otherwise
       cp_async16(raw_base + raw_off[i], ptr[i], is_last ? tail[i] : full[i]);
       ptr[i] += stride[i];
@@ -156,12 +161,12 @@ struct OperandThread {
 };
 
 // MODE 0: NT (A[M,K], B[N,K])   1: NN (A[M,K], B[K,N])   2: TN (A[K,M], B[K,N])
-template <int MODE>
-__global__ void __launch_bounds__(UG_ALL_THREADS, 2) umma_gemm_kernel(UGemmArgs p) {
-  constexpr int BN = UG_BN;
-  using LY = UGLayout<MODE>;
+template <int MODE, int BN>
+__global__ void __launch_bounds__(UG_ALL_THREADS, BN <= 128 ? 2 : 1) umma_gemm_kernel(UGemmArgs p) {
+  using LY = UGLayout<MODE, BN>;
   constexpr bool A_KMAJ = LY::A_KMAJ, B_KMAJ = LY::B_KMAJ;
   constexpr int UG_A_PART = LY::A_PART, UG_B_PART = LY::B_PART, UG_STAGE_BYTES = LY::STAGE_BYTES, UG_DEPTH = LY::DEPTH;
+  constexpr int UG_RAW_STAGE = LY::RAW_STAGE, UG_CORR_COL = LY::CORR_COL, UG_TMEM_COLS = LY::TMEM_COLS, NPB = LY::NPB;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_free[UG_STAGES];   // tensor core -> converters: stage may be overwritten
   __shared__ __align__(8) uint64_t bar_full[UG_STAGES];   // converters -> issuer: stage holds chunk c (256 arrivals)
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(UG_ALL_THREADS, 2) umma_gemm_kernel(UGemmArgs 
   OperandThread<128, A_KMAJ> oa;
   OperandThread<BN, B_KMAJ> ob;
   oa.init(p.A, p.lda, m0, p.M, kb, ke, nchunks, 0);
-  ob.init(p.B, p.ldb, n0, p.N, kb, ke, nchunks, 2);
+  ob.init(p.B, p.ldb, n0, p.N, kb, ke, nchunks, 2);      // B pieces use ring slots 2 .. 2+NPB-1
   const uint32_t raw_u32 = umma::smem_u32(smem + UG_STAGES * UG_STAGE_BYTES);
   uint8_t* const raw_ptr = smem + UG_STAGES * UG_STAGE_BYTES;
 
@@ -262,20 +267,20 @@ __global__ void __launch_bounds__(UG_ALL_THREADS, 2) umma_gemm_kernel(UGemmArgs 
     cp_async_wait<UG_DEPTH - 1>();                        // this thread's pieces of chunk c have landed
     UG_STAMP();                                           // [2] landed
     const uint8_t* raw = raw_ptr + ring_r * UG_RAW_STAGE;
-    float4 va[2], vb[2];
+    float4 va[2], vb[NPB];
 #pragma unroll
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 2; i++)
       va[i] = a_vec ? *reinterpret_cast<const float4*>(raw + oa.raw_off[i]) : oa.read_scalar(i, is_last);
+#pragma unroll
+    for (int i = 0; i < NPB; i++)
       vb[i] = b_vec ? *reinterpret_cast<const float4*>(raw + ob.raw_off[i]) : ob.read_scalar(i, is_last);
-    }
     if (c >= UG_STAGES) umma::mbar_wait(&bar_free[s], free_parity);   // MMAs of chunk c-2 released stage s
     UG_STAMP();                                           // [3] stage free
     uint8_t* st = smem + s * UG_STAGE_BYTES;
 #pragma unroll
-    for (int i = 0; i < 2; i++) {
-      oa.convert(i, va[i], st, st + UG_A_PART);
-      ob.convert(i, vb[i], st + 2 * UG_A_PART, st + 2 * UG_A_PART + UG_B_PART);
-    }
+    for (int i = 0; i < 2; i++) oa.convert(i, va[i], st, st + UG_A_PART);
+#pragma unroll
+    for (int i = 0; i < NPB; i++) ob.convert(i, vb[i], st + 2 * UG_A_PART, st + 2 * UG_A_PART + UG_B_PART);
     UG_STAMP();                                           // [4] converted + stored
     umma::fence_proxy_async_smem();                       // my generic-proxy writes -> visible to the tensor core
     UG_STAMP();                                           // [5] fenced
@@ -291,11 +296,12 @@ __global__ void __launch_bounds__(UG_ALL_THREADS, 2) umma_gemm_kernel(UGemmArgs 
   umma::tc_fence_after_sync();
   UG_STAMP();
 
-  // ---- epilogue: thread = output row (TMEM lane 32*(warp%4)+lane); warps 0-3 take column chunks 0..3, warps 4-7 chunks 4..6 ----
+  // ---- epilogue: thread = output row (TMEM lane 32*(warp%4)+lane); the two warp groups split the columns ----
   const int row = m0 + (warp & 3) * 32 + lane;
   const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const bool c_vec = (p.splits <= 1) && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-  const int cb_begin = (warp < 4) ? 0 : 64, cb_end = (warp < 4) ? 64 : BN;
+  constexpr int HALF = ((BN / 2 + 15) / 16) * 16;        // warps 0-3: columns [0, HALF), warps 4-7: [HALF, BN)
+  const int cb_begin = (warp < 4) ? 0 : HALF, cb_end = (warp < 4) ? HALF : BN;
 #pragma unroll 1
   for (int cb = cb_begin; cb < cb_end; cb += 16) {
     if (n0 + cb >= p.N) break;                      // warp-uniform
@@ -358,17 +364,25 @@ __global__ void ug_scale2d_kernel(float* C, i64 ldc, int M, int N, float beta) {
   *c = (beta == 0.f) ? 0.f : beta * *c;
 }
 
-template <int MODE>
+template <int MODE, int BN>
 static int launch_umma(const UGemmArgs& p, cudaStream_t st) {
+  using LY = UGLayout<MODE, BN>;
   static bool configured = false;
   if (!configured) {
-    MMDFN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, UGLayout<MODE>::SMEM));
+    MMDFN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY::SMEM));
     configured = true;
   }
-  dim3 grid(ceil_div(p.M, 128), ceil_div(p.N, UG_BN), p.splits > 1 ? p.splits : 1);
-  umma_gemm_kernel<MODE><<<grid, UG_ALL_THREADS, UGLayout<MODE>::SMEM, st>>>(p);
+  dim3 grid(ceil_div(p.M, 128), ceil_div(p.N, BN), p.splits > 1 ? p.splits : 1);
+  umma_gemm_kernel<MODE, BN><<<grid, UG_ALL_THREADS, LY::SMEM, st>>>(p);
   MMDFN_LAUNCH_CHECK();
   return 0;
+}
+
+template <int MODE>
+static int dispatch_bn(const UGemmArgs& p, int bn, cudaStream_t st) {
+  if (bn == 112) return launch_umma<MODE, 112>(p, st);
+  if (bn == 160) return launch_umma<MODE, 160>(p, st);
+  return launch_umma<MODE, 224>(p, st);
 }
 
 static long long* g_ug_dbg = nullptr;
@@ -381,10 +395,18 @@ int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A
   if (!A || !B || !C) return MMDFN_ENULL;
   if (tb && ta) return MMDFN_EINVAL;
   UGemmArgs p{A, lda, B, ldb, C, ldc, bias, M, N, K, alpha, beta, act, 1, g_ug_variant, g_ug_dbg};
-  const i64 tiles = (i64)ceil_div(M, 128) * ceil_div(N, UG_BN);
-  // split the contraction when the output has fewer tiles than two waves of 2 CTAs/SM (weight gradients)
-  if (tiles < 296 && K >= 512 && bias == nullptr && act == 0) {
-    i64 s = ceil_div64(592, tiles);
+  // column tile: 112 unless a width is forced through mmdfn_gemm_tc_set_variant (profiling aid)
+  int bn = 112;
+  if (g_ug_variant == 112 || g_ug_variant == 160 || g_ug_variant == 224) {
+    bn = g_ug_variant;
+  }
+  // measured on B200 (tools/umma_check.py, 153600x300x200): 112 -> 336 us, 160 -> 376 us, 224 -> 406 us: two
+  // co-resident narrow CTAs hide each other's conversion latency better than one wide CTA amortises operand traffic
+  const i64 tiles = (i64)ceil_div(M, 128) * ceil_div(N, bn);
+  const i64 per_wave = bn == 112 ? 296 : 148;
+  // split the contraction when the output has fewer tiles than two waves (weight gradients)
+  if (tiles < per_wave && K >= 512 && bias == nullptr && act == 0) {
+    i64 s = ceil_div64(2 * per_wave, tiles);
     const i64 smax = ceil_div(K, 128);
     p.splits = (int)(s < smax ? s : smax);
     if (p.splits < 1) p.splits = 1;
@@ -393,9 +415,9 @@ int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A
     ug_scale2d_kernel<<<(unsigned)ceil_div64((i64)M * N, 256), 256, 0, st>>>(C, ldc, M, N, beta);
     MMDFN_LAUNCH_CHECK();
   }
-  if (!ta && tb) return launch_umma<0>(p, st);
-  if (!ta && !tb) return launch_umma<1>(p, st);
-  return launch_umma<2>(p, st);
+  if (!ta && tb) return dispatch_bn<0>(p, bn, st);
+  if (!ta && !tb) return dispatch_bn<1>(p, bn, st);
+  return dispatch_bn<2>(p, bn, st);
 }
 
 }  // namespace mmdfn

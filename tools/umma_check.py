@@ -58,4 +58,15 @@ run("TN dW_ih splitK", 1, 0, 300, 200, 19200)
 run("TN dW small", 1, 0, 100, 100, 9600, beta=1.0)
 run("TN dW proj", 1, 0, 200, 1024, 3200)
 run("TN ragged", 1, 0, 77, 45, 190)
+for bn in (112, 160, 224):
+    L.call("mmdfn_gemm_tc_set_variant", bn)
+    print(f"--- forced BN={bn}")
+    run("NT gru in-gemm", 0, 1, 19200, 300, 200, bias=True)
+    run("NT ragged", 0, 1, 130, 100, 100, bias=True, act=1, beta=0.5, alpha=0.7)
+    run("NT big", 0, 1, 153600, 300, 200, bias=True)
+    run("NN dx", 0, 0, 19200, 200, 300)
+    run("NN ragged", 0, 0, 77, 45, 19)
+    run("TN dW_ih splitK", 1, 0, 300, 200, 19200)
+    run("TN ragged", 1, 0, 277, 245, 190)
+L.call("mmdfn_gemm_tc_set_variant", 0)
 print("done")
