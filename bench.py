@@ -217,7 +217,10 @@ def roofline_graph_conv(dev, n_dialogues=DIALOGUES_PER_GPU):
     peak, how = measured_peak_gbs()
     achieved = alg_bytes / (us * 1e-6) / 1e9
     return {"kernel": "adj_spmm_kernel (k6 graph-conv message aggregate hi = A_hat z, fp32)", "bound": "hbm",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel inside a training step
+            # (ncu --set full, profiles/r01_ncu_adj_spmm100_final.csv; z and A_hat are partly L2-resident there)
+            "traffic": 7767296 if n_dialogues == DIALOGUES_PER_GPU else None,
             "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us, "peak_source": how,
             "note": "launch covers one GCN layer of the %dx100 shard; operands rotated over %d copies (> L2)" % (n_dialogues, copies)}
 

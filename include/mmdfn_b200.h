@@ -94,6 +94,13 @@ int mmdfn_party_pack_bwd(int T, int B, int S, int N, const int* dia_off, const i
                          const float* dX, float wa, float wv, float wl, float* dbase_a, float* dbase_v,
                          float* dbase_l, float* dQ, void* stream);
 
+/* padded (T,B,D) view of one modality for the relation path's edge attention: rows t < L_b from the packed graph
+ * input, the padded tail from pad_src (the padded encoder output); and its adjoint ("=" on both outputs). */
+int mmdfn_unpack_pad_fwd(int T, int B, int D, const int* dia_off, const float* packed, const float* pad_src, float* out,
+                         void* stream);
+int mmdfn_unpack_pad_bwd(int T, int B, int D, const int* dia_off, const float* dM, float* d_packed, float* d_pad,
+                         void* stream);
+
 /* ---- k5: MM_GCN.create_big_adj in block-compact form (code/model_mm.py:122-180) ---------------
  * blk_off (B+1) int64: float offset of dialogue b's 3 blocks (3*L_b^2 floats each dialogue).
  * adj_blk: sum_b 3 L_b^2; adj_diag (3,N) pairs (a,v),(a,l),(v,l); dinv, rinv (3N); cos_blk, cos_diag
@@ -140,10 +147,11 @@ int mmdfn_gcn_stack_bwd(int B, int N, int Lmax, const int* dia_off, const long l
                         void* stream);
 
 /* ---- k9: head + loss (code/model.py:1328-1337 ; code/loss.py:14-34) ---------------------------
- * F (3N,300); mask (N,900) keep bytes or NULL; Wc (C,900); R (3N,300) saved; log_prob (N,C). C <= 16. */
-int mmdfn_head_fwd(int N, int C, const float* F, const unsigned char* mask, float mask_scale, const float* Wc,
-                   const float* bc, float* R, float* log_prob, void* stream);
-int mmdfn_head_bwd(int N, int C, const unsigned char* mask, float mask_scale, const float* Wc, const float* R,
+ * F (3N,300); mask (N,900) keep bytes or NULL; Wc (C,900); R (3N,300) saved; log_prob (N,C). C <= 16.
+ * relu = 1 on the GDF path (:1329), 0 on the relation path (:1241-1242: dropout -> smax_fc, no ReLU). */
+int mmdfn_head_fwd(int N, int C, const float* F, const unsigned char* mask, float mask_scale, int relu,
+                   const float* Wc, const float* bc, float* R, float* log_prob, void* stream);
+int mmdfn_head_bwd(int N, int C, const unsigned char* mask, float mask_scale, int relu, const float* Wc, const float* R,
                    const float* log_prob, const float* dlog_prob, float* dF, float* dWc, float* dbc,
                    int grads_zeroed, float* dlogits_ws, void* stream);
 int mmdfn_focal_loss_fwd(int N, int C, const float* log_prob, const long long* target, const float* alpha,

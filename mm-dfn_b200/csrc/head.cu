@@ -12,7 +12,7 @@ constexpr int MAXC = 16;
 
 // R[(m*N+n), k] = relu(F[(m*N+n), k] * mask[n, m*300+k] * scale)
 __global__ void head_relu_kernel(int N, const float* __restrict__ F, const unsigned char* __restrict__ mask,
-                                 float scale, float* __restrict__ R) {
+                                 float scale, int relu, float* __restrict__ R) {
   const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (i64)3 * N * HF) return;
   const i64 row = idx / HF;
@@ -21,7 +21,7 @@ __global__ void head_relu_kernel(int N, const float* __restrict__ F, const unsig
   const i64 n = row - (i64)m * N;
   float v = F[idx];
   if (mask) v = mask[n * 900 + m * HF + k] ? v * scale : 0.f;
-  R[idx] = fmaxf(v, 0.f);
+  R[idx] = relu ? fmaxf(v, 0.f) : v;
 }
 
 // in-place row-wise log_softmax over C (thread per row)
@@ -47,11 +47,21 @@ __global__ void log_softmax_bwd_kernel(int N, int C, const float* __restrict__ l
   for (int c = 0; c < C; c++) dlogits[(i64)n * C + c] = dlp[(i64)n * C + c] - expf(lp[(i64)n * C + c]) * s;
 }
 
-// dF = dR * [R > 0] * (mask ? scale : 1), in place on dF
-__global__ void head_relu_bwd_kernel(i64 n, const float* __restrict__ R, float scale, float* __restrict__ dF) {
+// dF = dR * [relu ? R > 0 : 1] * (mask ? keep * scale : 1), in place on dF
+__global__ void head_relu_bwd_kernel(int N, const float* __restrict__ R, const unsigned char* __restrict__ mask,
+                                     float scale, int relu, float* __restrict__ dF) {
   const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  dF[idx] = R[idx] > 0.f ? dF[idx] * scale : 0.f;
+  if (idx >= (i64)3 * N * HF) return;
+  float g = dF[idx];
+  if (mask) {
+    const i64 row = idx / HF;
+    const int k = (int)(idx - row * HF);
+    const int m = (int)(row / N);
+    const i64 n = row - (i64)m * N;
+    g = mask[n * 900 + m * HF + k] ? g * scale : 0.f;
+  }
+  if (relu && !(R[idx] > 0.f)) g = 0.f;
+  dF[idx] = g;
 }
 
 // loss = (mean|sum)_n -(1-pt)^gamma * alpha[y] * lp[n,y],  pt = exp(lp[n,y]) (no gradient through pt)
@@ -127,13 +137,13 @@ __global__ void adam_kernel(i64 n, float* __restrict__ p, const float* __restric
 
 using namespace mmdfn;
 
-extern "C" int mmdfn_head_fwd(int N, int C, const float* F, const unsigned char* mask, float mask_scale,
+extern "C" int mmdfn_head_fwd(int N, int C, const float* F, const unsigned char* mask, float mask_scale, int relu,
                               const float* Wc, const float* bc, float* R, float* log_prob, void* stream) {
   if (!F || !Wc || !bc || !R || !log_prob) return MMDFN_ENULL;
   if (C <= 0 || C > MAXC || N < 0) return MMDFN_EINVAL;
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  head_relu_kernel<<<(unsigned)ceil_div64((i64)3 * N * HF, 256), 256, 0, st>>>(N, F, mask, mask_scale, R);
+  head_relu_kernel<<<(unsigned)ceil_div64((i64)3 * N * HF, 256), 256, 0, st>>>(N, F, mask, mask_scale, relu, R);
   MMDFN_LAUNCH_CHECK();
   for (int m = 0; m < 3; m++)
     MMDFN_TRY(gemm(false, true, N, C, HF, 1.f, R + (i64)m * N * HF, HF, Wc + m * HF, 3 * HF, m ? 1.f : 0.f, log_prob, C,
@@ -144,7 +154,7 @@ extern "C" int mmdfn_head_fwd(int N, int C, const float* F, const unsigned char*
 }
 
 // dlogits_ws: (N, C) scratch.  dF (3N,300), dWc (C,900), dbc (C) are overwritten.
-extern "C" int mmdfn_head_bwd(int N, int C, const unsigned char* mask, float mask_scale, const float* Wc,
+extern "C" int mmdfn_head_bwd(int N, int C, const unsigned char* mask, float mask_scale, int relu, const float* Wc,
                               const float* R, const float* log_prob, const float* dlog_prob, float* dF, float* dWc,
                               float* dbc, int grads_zeroed, float* dlogits_ws, void* stream) {
   if (!Wc || !R || !log_prob || !dlog_prob || !dF || !dWc || !dbc || !dlogits_ws) return MMDFN_ENULL;
@@ -163,7 +173,7 @@ extern "C" int mmdfn_head_bwd(int N, int C, const unsigned char* mask, float mas
     MMDFN_TRY(gemm(true, false, C, HF, N, 1.f, dlogits_ws, C, R + (i64)m * N * HF, HF, gb, dWc + m * HF, 3 * HF, nullptr, 0, st));
     MMDFN_TRY(gemm(false, false, N, HF, C, 1.f, dlogits_ws, C, Wc + m * HF, 3 * HF, 0.f, dF + (i64)m * N * HF, HF, nullptr, 0, st));
   }
-  head_relu_bwd_kernel<<<(unsigned)ceil_div64((i64)3 * N * HF, 256), 256, 0, st>>>((i64)3 * N * HF, R, mask ? mask_scale : 1.f, dF);
+  head_relu_bwd_kernel<<<(unsigned)ceil_div64((i64)3 * N * HF, 256), 256, 0, st>>>(N, R, mask, mask_scale, relu, dF);
   MMDFN_LAUNCH_CHECK();
   return 0;
 }

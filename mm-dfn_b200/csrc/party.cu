@@ -121,6 +121,36 @@ __global__ void party_pack_bwd_kernel(PackBwdArgs p) {
   }
 }
 
+// padded (T,B,D) view of one modality: rows t < L_b come from the packed graph input, the padded tail from `pad_src`
+// (relation graph type: MaskedEdgeAttention soft-maxes over all T rows of the padded encoder output, code/model.py:449)
+__global__ void unpack_pad_kernel(int T, int B, int D, const int* __restrict__ dia_off, const float* __restrict__ packed,
+                                  const float* __restrict__ pad_src, float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.y + threadIdx.y;
+  const int b = blockIdx.y;
+  if (t >= T) return;
+  const int off = dia_off[b], L = dia_off[b + 1] - off;
+  const float* src = t < L ? packed + (i64)(off + t) * D : pad_src + ((i64)t * B + b) * D;
+  float* dst = out + ((i64)t * B + b) * D;
+  for (int c = threadIdx.x; c < D; c += 32) dst[c] = src[c];
+}
+
+// adjoint: d_packed[off+t] = dM[t,b] (t < L) ; d_pad[t,b] = t < L ? 0 : dM[t,b]
+__global__ void unpack_pad_bwd_kernel(int T, int B, int D, const int* __restrict__ dia_off, const float* __restrict__ dM,
+                                      float* __restrict__ d_packed, float* __restrict__ d_pad) {
+  const int t = blockIdx.x * blockDim.y + threadIdx.y;
+  const int b = blockIdx.y;
+  if (t >= T) return;
+  const int off = dia_off[b], L = dia_off[b + 1] - off;
+  const float* g = dM + ((i64)t * B + b) * D;
+  float* dp = d_pad + ((i64)t * B + b) * D;
+  if (t < L) {
+    float* dk = d_packed + (i64)(off + t) * D;
+    for (int c = threadIdx.x; c < D; c += 32) { dk[c] = g[c]; dp[c] = 0.f; }
+  } else {
+    for (int c = threadIdx.x; c < D; c += 32) dp[c] = g[c];
+  }
+}
+
 }  // namespace mmdfn
 
 using namespace mmdfn;
@@ -163,6 +193,24 @@ extern "C" int mmdfn_party_pack_bwd(int T, int B, int S, int N, const int* dia_o
   if (dQ) MMDFN_TRY(fill_zero(dQ, (size_t)T * 3 * B * S * 200 * sizeof(float), st));
   PackBwdArgs a{T, B, S, N, dia_off, sel, pos, dX, {wa, wv, wl}, {dbase_a, dbase_v, dbase_l}, dQ};
   party_pack_bwd_kernel<<<dim3(ceil_div(T, 8), B, 3), dim3(32, 8), 0, st>>>(a);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmdfn_unpack_pad_fwd(int T, int B, int D, const int* dia_off, const float* packed, const float* pad_src,
+                                    float* out, void* stream) {
+  if (!dia_off || !packed || !pad_src || !out) return MMDFN_ENULL;
+  if (T <= 0 || B <= 0) return 0;
+  unpack_pad_kernel<<<dim3(ceil_div(T, 8), B), dim3(32, 8), 0, (cudaStream_t)stream>>>(T, B, D, dia_off, packed, pad_src, out);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmdfn_unpack_pad_bwd(int T, int B, int D, const int* dia_off, const float* dM, float* d_packed,
+                                    float* d_pad, void* stream) {
+  if (!dia_off || !dM || !d_packed || !d_pad) return MMDFN_ENULL;
+  if (T <= 0 || B <= 0) return 0;
+  unpack_pad_bwd_kernel<<<dim3(ceil_div(T, 8), B), dim3(32, 8), 0, (cudaStream_t)stream>>>(T, B, D, dia_off, dM, d_packed, d_pad);
   MMDFN_LAUNCH_CHECK();
   return 0;
 }

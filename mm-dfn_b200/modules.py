@@ -310,12 +310,12 @@ class DialogueGNNModel(nn.Module):
                  av_using_lstm=False, Deep_GCN_nlayers=64, dataset='IEMOCAP', use_speaker=True, use_modal=False,
                  reason_flag=False, multi_modal=True, use_crn_speaker=False, speaker_weights='1-1-1', modal_weight=1.0):
         super().__init__()
-        if base_model != 'LSTM' or not multi_modal or sorted(modals) != ['a', 'l', 'v'] or graph_type != 'GDF' \
-                or att_type != 'concat_subsequently' or av_using_lstm or D_e != 100 or graph_hidden_size != 100 \
-                or not use_residue:
+        if base_model != 'LSTM' or not multi_modal or sorted(modals) != ['a', 'l', 'v'] \
+                or graph_type not in ('GDF', 'relation') or att_type != 'concat_subsequently' or av_using_lstm \
+                or D_e != 100 or graph_hidden_size != 100 or not use_residue or (graph_type == 'relation' and use_GCN):
             raise NotImplementedError(
                 "mmdfn_b200 implements the MM-DFN hot path only: base_model='LSTM', multi_modal, modals='avl', "
-                "graph_type='GDF', att_type='concat_subsequently', D_e=graph_hidden_size=100, use_residue")
+                "graph_type='GDF' (or 'relation'), att_type='concat_subsequently', D_e=graph_hidden_size=100, use_residue")
         self.base_model, self.avec, self.no_cuda, self.graph_type = base_model, avec, no_cuda, graph_type
         self.alpha, self.lamda, self.multiheads, self.graph_construct = alpha, lamda, multiheads, graph_construct
         self.use_topic, self.dropout, self.use_GCN, self.use_residue = use_topic, dropout, use_GCN, use_residue
@@ -339,13 +339,25 @@ class DialogueGNNModel(nn.Module):
         self.lstm_l = nn.GRU(input_size=200, hidden_size=D_e, num_layers=2, bidirectional=True, dropout=dropout)
         self.rnn_parties = nn.GRU(input_size=200, hidden_size=D_e, num_layers=2, bidirectional=True, dropout=dropout)
         self.att_model = MaskedEdgeAttention(2 * D_e, max_seq_len, self.no_cuda)
-        self.graph_model = MM_GCN(a_dim=2 * D_e, v_dim=2 * D_e, l_dim=2 * D_e, n_dim=2 * D_e, nlayers=Deep_GCN_nlayers,
-                                  nhidden=graph_hidden_size, nclass=n_classes, dropout=self.dropout, lamda=self.lamda,
-                                  alpha=self.alpha, variant=True, return_feature=self.return_feature,
-                                  use_residue=self.use_residue, n_speakers=n_speakers, modals=self.modals,
-                                  use_speaker=self.use_speaker, use_modal=self.use_modal, reason_flag=self.reason_flag,
-                                  modal_weight=self.modal_weight)
-        print("construct " + self.graph_type)
+        if graph_type == 'relation':
+            # code/model.py:917-929: one RGCN->GraphConv network per modality over the windowed speaker/temporal edges
+            from .relation import GraphNetwork
+            n_relations = 2 * n_speakers ** 2
+            self.graph_net_a = GraphNetwork(2 * D_e, n_classes, n_relations, max_seq_len, graph_hidden_size, dropout,
+                                            self.no_cuda, self.use_GCN, self.return_feature)
+            self.graph_net_v = GraphNetwork(2 * D_e, n_classes, n_relations, max_seq_len, graph_hidden_size, dropout,
+                                            self.no_cuda, self.use_GCN, self.return_feature)
+            self.graph_net_l = GraphNetwork(2 * D_e, n_classes, n_relations, max_seq_len, graph_hidden_size, dropout,
+                                            self.no_cuda, self.use_GCN, self.return_feature)
+            print("construct relation graph")
+        else:
+            self.graph_model = MM_GCN(a_dim=2 * D_e, v_dim=2 * D_e, l_dim=2 * D_e, n_dim=2 * D_e, nlayers=Deep_GCN_nlayers,
+                                      nhidden=graph_hidden_size, nclass=n_classes, dropout=self.dropout, lamda=self.lamda,
+                                      alpha=self.alpha, variant=True, return_feature=self.return_feature,
+                                      use_residue=self.use_residue, n_speakers=n_speakers, modals=self.modals,
+                                      use_speaker=self.use_speaker, use_modal=self.use_modal, reason_flag=self.reason_flag,
+                                      modal_weight=self.modal_weight)
+            print("construct " + self.graph_type)
         self.edge_type_mapping = {}
         for j in range(n_speakers):
             for k in range(n_speakers):
@@ -361,7 +373,7 @@ class DialogueGNNModel(nn.Module):
     def forward(self, U, qmask, umask, seq_lengths, U_a=None, U_v=None, test_label=False, masks=None):
         """U = text (T,B,D_m), U_a = audio, U_v = visual, qmask (T,B,S) -> (log_prob (N,C), None x4).
         `masks` (tests only): injected uint8 keep-masks {'gru_l','gru_p','gcn':{...},'head'}."""
-        if self.use_speaker or self.use_modal:
+        if (self.use_speaker or self.use_modal) and self.graph_type == 'GDF':
             raise NotImplementedError("use_speaker / use_modal are off on the MM-DFN path")
         if not U.is_cuda:
             raise ops.MMDFNError("DialogueGNNModel.forward needs CUDA tensors: the B200 path has no CPU fallback")
@@ -400,11 +412,31 @@ class DialogueGNNModel(nn.Module):
             E_l.record_stream(main)
         # k3/k4: scatter + speaker-weight combine + ragged pack, written as the stacked graph input
         X = ops.PartyPackFn.apply(Utab, E_l, Q, geom, sel, pos, S, tuple(self.speaker_weights))
+        m_h = ops.make_mask((geom.N, 900), p, dev) if train_drop else mk.get("head")
+        if self.graph_type == 'relation':
+            return self._forward_relation(X, E_l, qmask, geom, seq_lengths, umask, m_h, scale)
         gm = mk.get("gcn") if masks is not None else None
         F_ = self.graph_model.forward_stacked(X, geom, gm)
-        m_h = ops.make_mask((geom.N, 900), p, dev) if train_drop else mk.get("head")
         log_prob = ops.HeadFn.apply(F_, geom.N, m_h, scale, self.smax_fc.weight, self.smax_fc.bias)
         return log_prob, None, None, None, None
+
+    def _forward_relation(self, X, E_l, qmask, geom, seq_lengths, umask, m_h, scale):
+        """graph_type='relation' (code/model.py:1182-1242): windowed speaker/temporal edges, edge weights from
+        MaskedEdgeAttention over the padded text-branch features (the reference calls batch_graphify once per modality
+        with the same att_model and keeps the last = 'l' result), one RGCNConv->GraphConv network per modality,
+        concat -> dropout -> smax_fc -> log_softmax (no ReLU on this branch)."""
+        from . import relation as rel
+        N = geom.N
+        xa, xv, xl = X[:N], X[N:2 * N], X[2 * N:]
+        M_l = ops.UnpackPadFn.apply(xl, E_l, geom)                                   # padded emotions_l (T,B,200)
+        edges = rel.EdgeSet(qmask, geom, self.window_past, self.window_future)
+        rel._node_speakers(edges, qmask)
+        edges.edge_index._mmdfn_edges = edges
+        edge_norm = rel.EdgeAttnFn.apply(M_l, self.att_model.scalar.weight, edges)
+        args = (edges.edge_index, edge_norm, edges.edge_type, seq_lengths, umask, self.nodal_attention, self.avec)
+        F_ = torch.cat([self.graph_net_a(xa, *args), self.graph_net_v(xv, *args), self.graph_net_l(xl, *args)], dim=0)
+        log_prob = ops.HeadFn.apply(F_, N, m_h, scale, self.smax_fc.weight, self.smax_fc.bias, False)
+        return log_prob, edges.edge_index, edge_norm, edges.edge_type, list(edges.counts)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -253,6 +253,27 @@ class PartyPackFn(torch.autograd.Function):
         return dU, dE, dQ, None, None, None, None, None
 
 
+class UnpackPadFn(torch.autograd.Function):
+    """packed (N,D) rows of one modality + padded tail of `pad_src` (T,B,D) -> padded (T,B,D)."""
+
+    @staticmethod
+    def forward(ctx, packed, pad_src, geom):
+        packed, pad_src = _f32c(packed), _f32c(pad_src)
+        T, B, D = pad_src.shape
+        out = _empty((T, B, D), packed.device)
+        call("mmdfn_unpack_pad_fwd", T, B, D, ptr(geom.dia_off, torch.int32), ptr(packed), ptr(pad_src), ptr(out), stream())
+        ctx.geom, ctx.shape, ctx.n = geom, (T, B, D), packed.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dM):
+        T, B, D = ctx.shape
+        dM = _f32c(dM)
+        d_packed, d_pad = _empty((ctx.n, D), dM.device), _empty((T, B, D), dM.device)
+        call("mmdfn_unpack_pad_bwd", T, B, D, ptr(ctx.geom.dia_off, torch.int32), ptr(dM), ptr(d_packed), ptr(d_pad), stream())
+        return d_packed, d_pad, None
+
+
 # ---------------------------------------------------------------------------------------------
 # k5: block-compact adjacency
 # ---------------------------------------------------------------------------------------------
@@ -387,14 +408,15 @@ class HeadFn(torch.autograd.Function):
     """log_softmax(relu(dropout([F_a | F_v | F_l])) Wc^T + bc)  (code/model.py:1328-1337)."""
 
     @staticmethod
-    def forward(ctx, F_, N, mask, mask_scale, Wc, bc):
+    def forward(ctx, F_, N, mask, mask_scale, Wc, bc, relu=True):
         F_, Wc, bc = _f32c(F_), _f32c(Wc), _f32c(bc)
         C = Wc.shape[0]
         R = _empty(F_.shape, F_.device)
         lp = _empty((N, C), F_.device)
-        call("mmdfn_head_fwd", N, C, ptr(F_), ptr(mask, U8), float(mask_scale), ptr(Wc), ptr(bc), ptr(R), ptr(lp), stream())
+        call("mmdfn_head_fwd", N, C, ptr(F_), ptr(mask, U8), float(mask_scale), int(relu), ptr(Wc), ptr(bc), ptr(R), ptr(lp),
+             stream())
         ctx.save_for_backward(R, lp, Wc)
-        ctx.mask, ctx.mask_scale, ctx.N = mask, float(mask_scale), N
+        ctx.mask, ctx.mask_scale, ctx.N, ctx.relu = mask, float(mask_scale), N, int(relu)
         return lp
 
     @staticmethod
@@ -407,9 +429,9 @@ class HeadFn(torch.autograd.Function):
         flat = torch.zeros(C * 900 + C, device=dev, dtype=F32)
         dWc, dbc = flat[:C * 900].view(C, 900), flat[C * 900:]
         scratch = _empty((max(N, 1), C), dev)
-        call("mmdfn_head_bwd", N, C, ptr(ctx.mask, U8), ctx.mask_scale, ptr(Wc), ptr(R), ptr(lp), ptr(dlp), ptr(dF),
+        call("mmdfn_head_bwd", N, C, ptr(ctx.mask, U8), ctx.mask_scale, ctx.relu, ptr(Wc), ptr(R), ptr(lp), ptr(dlp), ptr(dF),
              ptr(dWc), ptr(dbc), 1, ptr(scratch), stream())
-        return dF, None, None, None, dWc, dbc
+        return dF, None, None, None, dWc, dbc, None
 
 
 class FocalLossFn(torch.autograd.Function):
