@@ -117,6 +117,11 @@ int mmdfn_adj_bwd(int B, int N, int Lmax, const int* dia_off, const long long* b
 int mmdfn_adj_densify(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* adj_blk,
                       const float* adj_diag, float* dense, void* stream);
 
+/* timing aid: 0 (default) = the aggregate runs on tcgen05 when G == 100 and every dialogue has <= 128 utterances,
+ * 1 = FFMA kernels only */
+int mmdfn_adj_spmm_set_variant(int variant);
+/* profiling aid: 64 x int64 device buffer receiving clock64() phase stamps of CTA 0 of the tcgen05 aggregate (NULL = off) */
+int mmdfn_adj_spmm_set_debug(long long* device_buf);
 /* ---- k6: message aggregate y = A_hat x, x,y (3N,G)  (torch.spmm, code/model_GCN.py:178) -------- */
 int mmdfn_adj_spmm(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* adj_blk,
                    const float* adj_diag, const float* x, int G, float* y, void* stream);

@@ -289,11 +289,16 @@ __global__ void __launch_bounds__(256) adj_spmm100_kernel(AdjGeom g, const float
   }
 }
 
+static int g_spmm_variant = 0;   // 0 = tensor cores when eligible, 1 = FFMA kernels only (A/B timing, tools/)
+
 int adj_spmm(int B, int N, int Lmax, const int* dia_off, const i64* blk_off, const float* adj_blk,
              const float* adj_diag, const float* x, int G, float* y, cudaStream_t st) {
   if (B <= 0 || N <= 0 || Lmax <= 0) return 0;
   AdjGeom g{B, N, dia_off, blk_off};
-  if (G == SP_G && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (G == SP_G && aligned && Lmax <= 128 && g_spmm_variant == 0)
+    return adj_spmm_tc(B, N, dia_off, blk_off, adj_blk, adj_diag, x, y, st);
+  if (G == SP_G && aligned) {
     static bool configured = false;
     if (!configured) {
       MMDFN_CUDA(cudaFuncSetAttribute(adj_spmm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
@@ -598,6 +603,12 @@ extern "C" int mmdfn_adj_bwd(int B, int N, int Lmax, const int* dia_off, const l
   MMDFN_LAUNCH_CHECK();
   adj_bwd_finish_kernel<<<ceil_div(N, 4), dim3(32, 4), 0, st>>>(N, X, rinv, cos_diag, d_diag, dinv, dd_ws, modal_weight, add, dX);
   MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmdfn_adj_spmm_set_variant(int variant) {
+  if (variant < 0 || variant > 1) return MMDFN_EINVAL;
+  mmdfn::g_spmm_variant = variant;
   return 0;
 }
 

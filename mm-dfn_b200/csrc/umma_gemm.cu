@@ -80,6 +80,11 @@ struct OperandThread {
   uint32_t raw_off[NP];   // staging slot offset inside a ring stage
   int st_off[NP];         // destination offset inside an operand part (-1: this thread has no such piece)
   int kofs[NP];
+  // !KMAJ, 16-byte aligned source: the staged chunk is a raw [k][row] tile (slot i' holds k = 8 (i' & 1) .. +7 of rows
+  // 128 (i' >> 1) .. +127, 512 B per k).  The K-major piece (row, k-quad) this thread converts is gathered from it with
+  // four conflict-free 32-bit loads (lanes = consecutive rows) and written with one 128-bit store per half.
+  int rd_off[NP];         // byte offset of (row, first k of the quad) inside a ring stage
+  int st_off_t[NP];       // destination of that piece (-1: none)
 
   __device__ __forceinline__ void init(const float* g, i64 ld, int row0, int row_end, int kb, int ke, int nchunks,
                                        int slot_base) {
@@ -110,6 +115,10 @@ struct OperandThread {
         stride[i] = ok ? (i64)UG_KC * ld * 4 : 0;
         full[i] = ok ? min(16, 4 * (row_end - row)) : 0;
         tail[i] = (k_last + kl < ke) ? full[i] : 0;
+        // conversion piece i: row 128 (i >> 1) + 32 (warp & 3) + lane, k-quad (warp >> 2) + 2 (i & 1)
+        const int rt = 128 * (i >> 1) + 32 * (warp & 3) + lane, q = (warp >> 2) + 2 * (i & 1);
+        rd_off[i] = ((slot_base + (q >> 1) + 2 * (i >> 1)) * UG_THREADS) * 16 + 4 * (q & 1) * 512 + (rt & 127) * 4;
+        st_off_t[i] = (rt < R) ? ((rt >> 3) * UG_SBO + q * UG_LBO + (rt & 7) * 16) : -1;
       }
     }
   }
@@ -136,6 +145,19 @@ struct OperandThread {
     if (nv > 3) v.w = q[3];
     ptr[i] += stride[i];
     return v;
+  }
+
+  // transposed gather of one K-major piece from the staged raw tile (all converters' copies must be visible)
+  __device__ __forceinline__ void convert_t(int i, const uint8_t* raw, uint8_t* hi, uint8_t* lo) const {
+    if (st_off_t[i] < 0) return;
+    const float* q = reinterpret_cast<const float*>(raw + rd_off[i]);
+    float4 h, l;
+    umma::split_tf32(q[0], h.x, l.x);
+    umma::split_tf32(q[128], h.y, l.y);
+    umma::split_tf32(q[256], h.z, l.z);
+    umma::split_tf32(q[384], h.w, l.w);
+    *reinterpret_cast<float4*>(hi + st_off_t[i]) = h;
+    *reinterpret_cast<float4*>(lo + st_off_t[i]) = l;
   }
 
   // split the piece into tf32 hi/lo and write both halves into the UMMA operand stage
@@ -262,25 +284,49 @@ __global__ void __launch_bounds__(UG_ALL_THREADS, BN <= 128 ? 2 : 1) umma_gemm_k
   for (int c = 0; c < nchunks; c++) {
     const bool is_last = (c == nchunks - 1);
     UG_STAMP();                                           // [0] loop top
-    stage_chunk(c + UG_DEPTH - 1);
-    UG_STAMP();                                           // [1] cp.async issued
-    cp_async_wait<UG_DEPTH - 1>();                        // this thread's pieces of chunk c have landed
+    if (MODE == 0) {
+      stage_chunk(c + UG_DEPTH - 1);
+      UG_STAMP();                                         // [1] cp.async issued
+      cp_async_wait<UG_DEPTH - 1>();                      // this thread's pieces of chunk c have landed
+    } else {
+      // transposed operands are gathered from other threads' staged pieces: chunk c must have landed for every
+      // converter, and the ring slot refilled below (chunk c-1's) must have been read by every converter
+      cp_async_wait<UG_DEPTH - 2>();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      UG_STAMP();                                         // [1] landed everywhere
+      stage_chunk(c + UG_DEPTH - 1);
+    }
     UG_STAMP();                                           // [2] landed
     const uint8_t* raw = raw_ptr + ring_r * UG_RAW_STAGE;
+    const bool a_t = !A_KMAJ && a_vec, b_t = !B_KMAJ && b_vec;
     float4 va[2], vb[NPB];
+    if (!a_t) {
 #pragma unroll
-    for (int i = 0; i < 2; i++)
-      va[i] = a_vec ? *reinterpret_cast<const float4*>(raw + oa.raw_off[i]) : oa.read_scalar(i, is_last);
+      for (int i = 0; i < 2; i++)
+        va[i] = a_vec ? *reinterpret_cast<const float4*>(raw + oa.raw_off[i]) : oa.read_scalar(i, is_last);
+    }
+    if (!b_t) {
 #pragma unroll
-    for (int i = 0; i < NPB; i++)
-      vb[i] = b_vec ? *reinterpret_cast<const float4*>(raw + ob.raw_off[i]) : ob.read_scalar(i, is_last);
+      for (int i = 0; i < NPB; i++)
+        vb[i] = b_vec ? *reinterpret_cast<const float4*>(raw + ob.raw_off[i]) : ob.read_scalar(i, is_last);
+    }
     if (c >= UG_STAGES) umma::mbar_wait(&bar_free[s], free_parity);   // MMAs of chunk c-2 released stage s
     UG_STAMP();                                           // [3] stage free
     uint8_t* st = smem + s * UG_STAGE_BYTES;
+    if (a_t) {
 #pragma unroll
-    for (int i = 0; i < 2; i++) oa.convert(i, va[i], st, st + UG_A_PART);
+      for (int i = 0; i < 2; i++) oa.convert_t(i, raw, st, st + UG_A_PART);
+    } else {
 #pragma unroll
-    for (int i = 0; i < NPB; i++) ob.convert(i, vb[i], st + 2 * UG_A_PART, st + 2 * UG_A_PART + UG_B_PART);
+      for (int i = 0; i < 2; i++) oa.convert(i, va[i], st, st + UG_A_PART);
+    }
+    if (b_t) {
+#pragma unroll
+      for (int i = 0; i < NPB; i++) ob.convert_t(i, raw, st + 2 * UG_A_PART, st + 2 * UG_A_PART + UG_B_PART);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NPB; i++) ob.convert(i, vb[i], st + 2 * UG_A_PART, st + 2 * UG_A_PART + UG_B_PART);
+    }
     UG_STAMP();                                           // [4] converted + stored
     umma::fence_proxy_async_smem();                       // my generic-proxy writes -> visible to the tensor core
     UG_STAMP();                                           // [5] fenced
@@ -319,9 +365,20 @@ __global__ void __launch_bounds__(UG_ALL_THREADS, BN <= 128 ? 2 : 1) umma_gemm_k
     if (row >= p.M) continue;
     float* crow = p.C + (i64)row * p.ldc + n0 + cb;
     if (p.splits > 1) {
+      // split-K partial sums: 128-bit vector reductions (4x fewer L2 reduction requests than scalar atomics; with one
+      // row per lane every request touches 32 different lines, so the request count is what the epilogue costs)
+      const bool r_vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((n0 & 3) == 0);
 #pragma unroll
-      for (int q = 0; q < 16; q++)
-        if (n0 + cb + q < p.N) atomicAdd(crow + q, p.alpha * v[q]);
+      for (int q4 = 0; q4 < 16; q4 += 4) {
+        if (r_vec && n0 + cb + q4 + 3 < p.N) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + q4), "f"(p.alpha * v[q4]),
+                       "f"(p.alpha * v[q4 + 1]), "f"(p.alpha * v[q4 + 2]), "f"(p.alpha * v[q4 + 3]) : "memory");
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            if (n0 + cb + q4 + q < p.N) atomicAdd(crow + q4 + q, p.alpha * v[q4 + q]);
+        }
+      }
       continue;
     }
 #pragma unroll
@@ -404,9 +461,11 @@ int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A
   // co-resident narrow CTAs hide each other's conversion latency better than one wide CTA amortises operand traffic
   const i64 tiles = (i64)ceil_div(M, 128) * ceil_div(N, bn);
   const i64 per_wave = bn == 112 ? 296 : 148;
-  // split the contraction when the output has fewer tiles than two waves (weight gradients)
-  if (tiles < per_wave && K >= 512 && bias == nullptr && act == 0) {
-    i64 s = ceil_div64(2 * per_wave, tiles);
+  // split the contraction when the output has fewer tiles than one wave (weight gradients): as many splits as fill
+  // one wave of co-resident CTAs -- every split pays a full-tile reduction epilogue (measured ~17 k cycles with scalar
+  // atomics, vs ~1.6 k per 16-wide K chunk), so more, shorter splits only add epilogues
+  if (tiles * 2 <= per_wave && K >= 512 && bias == nullptr && act == 0) {
+    i64 s = per_wave / tiles;
     const i64 smax = ceil_div(K, 128);
     p.splits = (int)(s < smax ? s : smax);
     if (p.splits < 1) p.splits = 1;

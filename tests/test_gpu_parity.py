@@ -265,6 +265,30 @@ def test_spmm_and_grad(lengths, G):
     assert maxerr(dg.grad, exp_dg) < 1e-4
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("lengths", [[100, 100], [128, 1, 37, 64, 99, 33, 2], [8], [127, 126, 125]])
+def test_aggregate_kernels_tensor_core_and_ffma(lengths, variant):
+    """The tcgen05 (3xTF32, variant 0) and FFMA (variant 1) aggregate kernels against an fp64 dense product: ragged
+    block sizes, lengths that are not multiples of 4 (scalar operand loads) and the 128-row maximum."""
+    mm, ops, L = _mods()
+    N = sum(lengths)
+    feats = [rnd(N, 200, seed=s) for s in (1, 2, 3)]
+    blocks, diags = O.adj_blocks(feats, lengths, 1.0)
+    blk_c, dg_c = blocks_flat(blocks, diags, lengths)
+    dense = O.blocks_to_dense(blocks, diags, lengths).double()
+    x = rnd(3 * N, 100, seed=7) * 3.0
+    geom = ops.DialogGeom(lengths, DEV)
+    y = torch.full((3 * N, 100), float("nan"), device=DEV)
+    L.call("mmdfn_adj_spmm_set_variant", variant)
+    try:
+        bd, dd, xd = blk_c.to(DEV), dg_c.to(DEV), x.to(DEV)
+        L.call("mmdfn_adj_spmm", *geom.args(), L.ptr(bd), L.ptr(dd), L.ptr(xd), 100, L.ptr(y), L.stream())
+        torch.cuda.synchronize()
+    finally:
+        L.call("mmdfn_adj_spmm_set_variant", 0)
+    assert float((y.cpu().double() - dense @ x.double()).abs().max()) < 5e-6
+
+
 def test_long_dialogues_chunked_paths():
     """L > 128 (BASELINE config 5 has 500-utterance dialogues): the aggregate's multi-chunk K loop, the adjacency
     kernels' multi-tile grids and their backward, against the oracle."""
