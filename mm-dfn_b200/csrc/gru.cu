@@ -4,10 +4,10 @@
 //
 // Design: the input-gate GEMM is hoisted out of the time loop (one dense GEMM per layer
 // over all rows).  One CTA owns NB sequences of one direction for the whole sequence:
-// each of 300 threads keeps one row of W_hh (100 floats) in registers, the NB hidden
-// states live in shared memory and are read as broadcast 128-bit loads, so the T-step
-// loop touches HBM only for the per-step gate rows (coalesced, prefetched before the
-// mat-vec) and the outputs.  For the speaker-party encoder the per-step rows are fetched
+// W_hh stays in registers (100 weights per thread, as packed pairs for fp32x2 FMAs) and
+// the NB hidden states live in shared memory (forward: a row per thread + broadcast
+// 128-bit loads; backward: a 25-wide slice of four outputs per thread + quad shuffles).  The T-step loop touches HBM only for the
+// per-step gate rows (coalesced, prefetched before the mat-vec) and the outputs.  For the speaker-party encoder the per-step rows are fetched
 // through `rowmap` (gather fused into the recurrence): the projected utterance table is
 // multiplied by W_ih once per utterance instead of once per (speaker, position) slot.
 #include "internal.cuh"
@@ -30,6 +30,9 @@ struct GruFwdArgs {
   float* gates;           // (T, nseq, 2, 400) r z n hn, nullable
 };
 
+// Forward recurrence: thread j < 300 keeps row j of W_hh in registers (50 packed pairs: the mat-vec runs on fp32x2
+// FMAs) and reads the NB hidden vectors as warp-broadcast 128-bit loads.  (The quad-sliced mapping the backward kernel
+// uses was measured slower here -- 160 vs 122 us at NB = 2: the forward step ends in a serial reduce -> gate chain.)
 template <int NB>
 __global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(GruFwdArgs p) {
   __shared__ __align__(16) float hs[NB][GH];
@@ -39,32 +42,35 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(GruFwdArgs p) {
   const int s0 = blockIdx.x * NB;
   const int nb = min(NB, p.nseq - s0);
   const int j = tid < G3 ? tid : G3 - 1;     // threads 300..319 only help in the pointwise phase
-  float w[GH];
+  float2 w2[GH / 2];
   {
     const float* wr = p.w_hh[dir] + (i64)j * GH;
 #pragma unroll
-    for (int k = 0; k < GH; k++) w[k] = wr[k];
+    for (int k = 0; k < GH / 2; k++) w2[k] = make_float2(wr[2 * k], wr[2 * k + 1]);
   }
   const float bh = p.b_hh[dir][j];
   const float bi = p.b_ih[dir] ? p.b_ih[dir][j] : 0.f;
   for (int i = tid; i < NB * GH; i += GRU_THREADS) (&hs[0][0])[i] = 0.f;
   __syncthreads();
 
-  // software pipeline: gate rows of step s+1 and row indices of step s+2 are in flight while step s computes
+  // software pipeline: gate rows of step s+1 and row indices of step s+2 are in flight while step s computes.  The
+  // row index stays a raw 32-bit value until it is used one step later: any arithmetic on it here (even the widening
+  // to 64 bits) makes the warp wait for the load on the spot (14 % of all stall samples in the first version).
   auto slot_of = [&](int step, int b) { return (i64)(dir ? (p.T - 1 - step) : step) * p.nseq + s0 + b; };
-  auto row_of = [&](int step, int b) -> i64 {
+  auto row_of = [&](int step, int b) -> int {           // -2: no such slot, -1: zero input (bias only), >= 0: row of xg
     if (step >= p.T || b >= nb) return -2;
     const i64 slot = slot_of(step, b);
-    return p.rowmap ? (i64)p.rowmap[slot] : slot;
+    return p.rowmap ? p.rowmap[slot] : (int)slot;
   };
-  auto gate_of = [&](i64 row) { return row >= 0 ? p.xg[row * 600 + dir * G3 + j] : (row == -1 ? bi : 0.f); };
+  auto gate_of = [&](int row) { return row >= 0 ? p.xg[(i64)row * 600 + dir * G3 + j] : (row == -1 ? bi : 0.f); };
   float xv[NB], xn[NB];
-  i64 rown[NB];
+  int rown[NB];
 #pragma unroll
   for (int b = 0; b < NB; b++) {
     xv[b] = gate_of(row_of(0, b));
     rown[b] = row_of(1, b);
   }
+#pragma unroll 1
   for (int step = 0; step < p.T; step++) {
     const int t = dir ? (p.T - 1 - step) : step;
 #pragma unroll
@@ -72,20 +78,21 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(GruFwdArgs p) {
       xn[b] = gate_of(rown[b]);          // consumed at the top of the next step
       rown[b] = row_of(step + 2, b);
     }
-    float acc[NB];
+    float2 acc2[NB];
 #pragma unroll
-    for (int b = 0; b < NB; b++) acc[b] = bh;
+    for (int b = 0; b < NB; b++) acc2[b] = make_float2(bh, 0.f);
 #pragma unroll
     for (int k = 0; k < GH; k += 4) {
 #pragma unroll
       for (int b = 0; b < NB; b++) {
         const float4 h4 = *reinterpret_cast<const float4*>(&hs[b][k]);
-        acc[b] = fmaf(w[k], h4.x, acc[b]);
-        acc[b] = fmaf(w[k + 1], h4.y, acc[b]);
-        acc[b] = fmaf(w[k + 2], h4.z, acc[b]);
-        acc[b] = fmaf(w[k + 3], h4.w, acc[b]);
+        acc2[b] = __ffma2_rn(w2[k / 2], make_float2(h4.x, h4.y), acc2[b]);
+        acc2[b] = __ffma2_rn(w2[k / 2 + 1], make_float2(h4.z, h4.w), acc2[b]);
       }
     }
+    float acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) acc[b] = acc2[b].x + acc2[b].y;
     if (tid < G3) {
 #pragma unroll
       for (int b = 0; b < NB; b++) {
@@ -119,6 +126,27 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(GruFwdArgs p) {
   }
 }
 
+// Mat-vec mapping of the backward recurrence.  A thread owns a 25-wide k slice of FOUR outputs (100 weights in
+// registers as 4 x 14 packed pairs, pads zero) and reads only its slice of the gate gradients (7 128-bit loads per
+// sequence instead of 25); the four lanes of a quad hold the four slices of the same outputs and combine their partial
+// sums with a 3-shuffle reduce-scatter, after which lane s of the quad owns finished output s (measured 171 vs 188 us).
+constexpr int GSL = 28;                 // padded slice length in shared memory (25 used + 3 zero)
+constexpr int GHP = 4 * GSL;            // padded 100-vector: slice s at [28 s, 28 s + 25)
+__device__ __forceinline__ int gru_hpos(int u) { return (u / 25) * GSL + (u % 25); }
+
+// sums v[i] over the 4 lanes of a quad; returns the total of row (lane & 3) in that lane
+__device__ __forceinline__ float quad_reduce_scatter(const float (&v)[4], int s) {
+  const bool b0 = s & 1, b1 = s & 2;
+  // xor 1: lanes with bit0 = 0 keep rows 0, 2 and receive the partner's; bit0 = 1 keep rows 1, 3
+  const float send0 = b0 ? v[0] : v[1], send1 = b0 ? v[2] : v[3];
+  const float keep0 = b0 ? v[1] : v[0], keep1 = b0 ? v[3] : v[2];
+  const float x0 = keep0 + __shfl_xor_sync(0xffffffffu, send0, 1);      // row b0       (0 or 1)
+  const float x1 = keep1 + __shfl_xor_sync(0xffffffffu, send1, 1);      // row 2 + b0   (2 or 3)
+  // xor 2: bit1 = 0 keeps x0, bit1 = 1 keeps x1
+  const float send = b1 ? x0 : x1, keep = b1 ? x1 : x0;
+  return keep + __shfl_xor_sync(0xffffffffu, send, 2);                  // row b0 + 2 b1 = s
+}
+
 struct GruBwdArgs {
   int T, nseq;
   const float* dy;      // (T, nseq, 200)
@@ -134,20 +162,32 @@ struct GruBwdArgs {
 template <int NB>
 __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(GruBwdArgs p) {
   __shared__ __align__(16) float dh[NB][GH];
-  __shared__ __align__(16) float dgh[NB][G3];
+  __shared__ __align__(16) float dgh[NB][3 * GHP];      // gate segment jp at [112 jp + gru_hpos(jj)], pads stay zero
   __shared__ __align__(16) float part[3][NB][GH];
   const int tid = threadIdx.x;
   const int dir = blockIdx.y;
   const int s0 = blockIdx.x * NB;
   const int nb = min(NB, p.nseq - s0);
-  const int u_mv = tid % GH;
-  const int jp = tid < G3 ? tid / GH : 2;
-  float w[GH];   // w[jj] = W_hh[jp*100 + jj][u]  (a column slice: computes W_hh^T dgh)
+  // W_hh^T dgh with the same quad mapping as the forward kernel: thread (jp, uq, sl) holds the 25-wide jj slice sl of
+  // gate segment jp for the four outputs u = uq + 25 i; lane sl of the quad finishes output uq + 25 sl
+  const bool mv_on = tid < G3;
+  const int jp = mv_on ? tid / GH : 2;
+  const int sl = tid & 3, uq = mv_on ? (tid % GH) >> 2 : 0;
+  const int u_f = uq + 25 * sl;
+  float2 w2[4][GSL / 2];
 #pragma unroll
-  for (int jj = 0; jj < GH; jj++) w[jj] = p.w_hh[dir][(i64)(jp * GH + jj) * GH + u_mv];
+  for (int i = 0; i < 4; i++) {
+    const int u = uq + 25 * i;
+#pragma unroll
+    for (int k = 0; k < GSL / 2; k++) {
+      const float* wc = p.w_hh[dir] + (i64)(jp * GH + 25 * sl) * GH + u;
+      w2[i][k] = make_float2((mv_on && 2 * k < 25) ? wc[(i64)(2 * k) * GH] : 0.f,
+                             (mv_on && 2 * k + 1 < 25) ? wc[(i64)(2 * k + 1) * GH] : 0.f);
+    }
+  }
   for (int i = tid; i < NB * GH; i += GRU_THREADS) (&dh[0][0])[i] = 0.f;
   for (int i = tid; i < 3 * NB * GH; i += GRU_THREADS) (&part[0][0][0])[i] = 0.f;
-  for (int i = tid; i < NB * G3; i += GRU_THREADS) (&dgh[0][0])[i] = 0.f;
+  for (int i = tid; i < NB * 3 * GHP; i += GRU_THREADS) (&dgh[0][0])[i] = 0.f;
   __syncthreads();
 
   constexpr int ITEMS = (NB * GH + GRU_THREADS - 1) / GRU_THREADS;
@@ -194,29 +234,32 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(GruBwdArgs p) {
       o[u] = dr_pre; o[GH + u] = dz_pre; o[2 * GH + u] = dn_pre;
       float* o2 = p.dgh + (slot * 2 + dir) * G3;
       o2[u] = dr_pre; o2[GH + u] = dz_pre; o2[2 * GH + u] = dhn_;
-      dgh[b][u] = dr_pre; dgh[b][GH + u] = dz_pre; dgh[b][2 * GH + u] = dhn_;
+      const int gp = gru_hpos(u);
+      dgh[b][gp] = dr_pre; dgh[b][GHP + gp] = dz_pre; dgh[b][2 * GHP + gp] = dhn_;
       dh[b][u] = dht * z;
       sb[it][0] += dr_pre; sb[it][1] += dz_pre; sb[it][2] += dn_pre; sb[it][3] += dhn_;
     }
     fetch(step + 1, nxt);                              // lands while the mat-vec below runs
     __syncthreads();
-    float acc[NB];
 #pragma unroll
-    for (int b = 0; b < NB; b++) acc[b] = 0.f;
+    for (int b = 0; b < NB; b++) {
+      float2 acc2[4];
 #pragma unroll
-    for (int k = 0; k < GH; k += 4) {
+      for (int i = 0; i < 4; i++) acc2[i] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int b = 0; b < NB; b++) {
-        const float4 d4 = *reinterpret_cast<const float4*>(&dgh[b][jp * GH + k]);
-        acc[b] = fmaf(w[k], d4.x, acc[b]);
-        acc[b] = fmaf(w[k + 1], d4.y, acc[b]);
-        acc[b] = fmaf(w[k + 2], d4.z, acc[b]);
-        acc[b] = fmaf(w[k + 3], d4.w, acc[b]);
+      for (int q = 0; q < GSL / 4; q++) {
+        const float4 d4 = *reinterpret_cast<const float4*>(&dgh[b][GHP * jp + GSL * sl + 4 * q]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          acc2[i] = __ffma2_rn(w2[i][2 * q], make_float2(d4.x, d4.y), acc2[i]);
+          acc2[i] = __ffma2_rn(w2[i][2 * q + 1], make_float2(d4.z, d4.w), acc2[i]);
+        }
       }
-    }
-    if (tid < G3) {
+      float pv[4];
 #pragma unroll
-      for (int b = 0; b < NB; b++) part[jp][b][u_mv] = acc[b];
+      for (int i = 0; i < 4; i++) pv[i] = acc2[i].x + acc2[i].y;
+      const float acc = quad_reduce_scatter(pv, sl);
+      if (mv_on) part[jp][b][u_f] = acc;
     }
     __syncthreads();
 #pragma unroll
@@ -254,13 +297,25 @@ __global__ void mask_mul_kernel(const float* __restrict__ x, const unsigned char
   if (i < n) y[i] = m[i] ? x[i] * scale : 0.f;
 }
 
+// Sequences per CTA.  The recurrence is issue-bound per CTA (100 FMAs per sequence per thread and step), so fewer
+// sequences per CTA shorten every step as long as the CTAs still fit in one wave; the text encoder and the party
+// encoder run concurrently on two streams, so a launch takes at most ~2/3 of the SMs (100 CTAs) before it widens its
+// tiles: text (32 sequences) -> NB 2 / 32 CTAs, party (192) -> NB 4 / 96 CTAs, more than 400 sequences -> NB 8.
+static int gru_pick_nb(int nseq) {
+  if (2 * ceil_div(nseq, 2) <= 100) return 2;
+  if (2 * ceil_div(nseq, 4) <= 100) return 4;
+  return (i64)ceil_div(nseq, 8) * 2 >= 148 ? 8 : 4;
+}
+
 static int launch_gru_fwd(const GruFwdArgs& a, cudaStream_t st) {
   if (a.T <= 0 || a.nseq <= 0) return 0;
-  // few sequences: smaller tiles -> more CTAs and a shorter per-step critical path
-  if ((i64)ceil_div(a.nseq, 8) * 2 >= 148) {
+  const int nb = gru_pick_nb(a.nseq);
+  if (nb == 8) {
     gru_fwd_kernel<8><<<dim3(ceil_div(a.nseq, 8), 2), GRU_THREADS, 0, st>>>(a);
-  } else {
+  } else if (nb == 4) {
     gru_fwd_kernel<4><<<dim3(ceil_div(a.nseq, 4), 2), GRU_THREADS, 0, st>>>(a);
+  } else {
+    gru_fwd_kernel<2><<<dim3(ceil_div(a.nseq, 2), 2), GRU_THREADS, 0, st>>>(a);
   }
   MMDFN_LAUNCH_CHECK();
   return 0;
@@ -268,10 +323,13 @@ static int launch_gru_fwd(const GruFwdArgs& a, cudaStream_t st) {
 
 static int launch_gru_bwd(const GruBwdArgs& a, cudaStream_t st) {
   if (a.T <= 0 || a.nseq <= 0) return 0;
-  if ((i64)ceil_div(a.nseq, 8) * 2 >= 148) {
+  const int nb = gru_pick_nb(a.nseq);
+  if (nb == 8) {
     gru_bwd_kernel<8><<<dim3(ceil_div(a.nseq, 8), 2), GRU_THREADS, 0, st>>>(a);
-  } else {
+  } else if (nb == 4) {
     gru_bwd_kernel<4><<<dim3(ceil_div(a.nseq, 4), 2), GRU_THREADS, 0, st>>>(a);
+  } else {
+    gru_bwd_kernel<2><<<dim3(ceil_div(a.nseq, 2), 2), GRU_THREADS, 0, st>>>(a);
   }
   MMDFN_LAUNCH_CHECK();
   return 0;

@@ -9,9 +9,12 @@
 // conflict-free 32-bit loads (lanes = consecutive columns) to form K-major pieces -- no conflicted scalar stores.
 // Warp-specialised like umma_gemm.cu: 8 converter warps fill a 2-stage operand ring (K chunks of 16), warp 8 issues
 // hi*hi into TMEM columns 0-111 and lo*hi, hi*lo into columns 128-239; tcgen05.commit releases stages.
-// Epilogue: tcgen05.ld into the (free again) raw z region as a row-major tile, then one coalesced pass adds the
-// cross-modal diagonal terms with 128-bit loads/stores.  112.6 KB of shared memory and 256 TMEM columns per CTA: two
-// CTAs per SM, so one block's loads and epilogue overlap the other's MMAs.
+// Epilogue: the cross-modal diagonal terms d[r] * z_n[r, :] need the other two modalities' z rows; their first batch
+// of 128-bit loads is issued BEFORE the wait for the last MMA, the accumulators go TMEM -> registers (thread = row)
+// -> a row-major tile in the free raw-z region, a coalesced pass adds the cross terms in shared memory, and ONE bulk
+// (TMA) store writes the block's L x 100 contiguous output rows.  (A cluster-of-3 variant that read the peers' raw z
+// through DSMEM was measured 2.3x slower: DSMEM delivers ~20 B/clk/SM, L2 ~64.)  112.6 KB of shared memory and 256
+// TMEM columns per CTA: two CTAs per SM, so one block's loads and epilogue overlap the other's MMAs.
 #include "umma.cuh"
 #include "internal.cuh"
 
@@ -54,6 +57,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) adj_spmm_tc_kernel(SpmmTcArgs p
   __shared__ __align__(8) uint64_t bar_full[2];
   __shared__ __align__(8) uint64_t bar_z[ST_NCH];             // one per 16-row chunk of the raw z copy (TMA bulk, single use)
   __shared__ uint32_t tmem_base_s;
+  __shared__ float dsm[2][ST_LMAX];                           // cross-modal diagonal entries of this block's rows
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / 3, m = blockIdx.x % 3;
   const int off = p.dia_off[b], L = p.dia_off[b + 1] - off;
@@ -113,6 +117,12 @@ __global__ void __launch_bounds__(ST_THREADS, 2) adj_spmm_tc_kernel(SpmmTcArgs p
       va[i] = v;
     }
   };
+  // cross-modal partners of modality m; their diagonal entries go to shared memory now (read by the epilogue)
+  const int o1 = (m == 0) ? 1 : 0, o2 = (m == 2) ? 1 : 2;
+  if (tid < 2 * ST_LMAX) {
+    const int r = tid & (ST_LMAX - 1), which = tid >> 7, o = which ? o2 : o1;
+    dsm[which][r] = (r < L) ? __ldg(p.adj_diag + (i64)st_pair_of(min(m, o), max(m, o)) * p.N + off + r) : 0.f;
+  }
   float4 va[ST_ADEPTH][2];
   if (warp < 8) {
     // rows L .. 16*nchunks-1 of the raw tile are read (as zeros) by the last chunk's transposed loads
@@ -212,6 +222,22 @@ __global__ void __launch_bounds__(ST_THREADS, 2) adj_spmm_tc_kernel(SpmmTcArgs p
       ST_STAMP();                                             // converted
     }
   }
+  // ---- epilogue ----
+  // cross-modal rows: float4 i of the block (row i / 25) for i = tid + u * 256; the first EB of them are requested
+  // before the wait for the last MMA so that their latency hides behind it
+  const float4* x1 = reinterpret_cast<const float4*>(p.x + ((i64)o1 * p.N + off) * ST_G);
+  const float4* x2 = reinterpret_cast<const float4*>(p.x + ((i64)o2 * p.N + off) * ST_G);
+  const int total = L * (ST_G / 4);
+  constexpr int EB = 5;
+  float4 a1[EB], a2[EB];
+#pragma unroll
+  for (int u = 0; u < EB; u++) {
+    const int i = tid + u * ST_CONV;
+    if (i < total) {
+      a1[u] = __ldg(x1 + i);
+      a2[u] = __ldg(x2 + i);
+    }
+  }
   if (nchunks > 0) {
     const int last = nchunks - 1;
     umma::mbar_wait(&bar_free[last & 1], (uint32_t)((last >> 1) & 1));
@@ -219,9 +245,9 @@ __global__ void __launch_bounds__(ST_THREADS, 2) adj_spmm_tc_kernel(SpmmTcArgs p
   umma::tc_fence_after_sync();
   ST_STAMP();                                                 // all MMAs done
 
-  // ---- epilogue 1: TMEM -> the (now free) raw z region as a row-major [r][100] tile ----
-  // thread = block row; warps 0-3 take columns 0..63, warps 4-7 columns 64..99.  Every converter passed the last
-  // full barrier before the final commit could fire, so nobody still reads rawz.
+  // TMEM -> the (now free) raw z region as a row-major [r][100] tile; thread = block row; warps 0-3 take columns
+  // 0..63, warps 4-7 columns 64..99.  Every converter passed the last full barrier before the final commit could
+  // fire, so nobody still reads rawz.
   {
     const int r = (warp & 3) * 32 + lane;
     const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -242,43 +268,42 @@ __global__ void __launch_bounds__(ST_THREADS, 2) adj_spmm_tc_kernel(SpmmTcArgs p
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");
   ST_STAMP();                                                 // tile in shared memory
-
-  // ---- epilogue 2: add the cross-modal diagonal terms, fully coalesced 128-bit traffic ----
   {
-    const int o1 = (m == 0) ? 1 : 0, o2 = (m == 2) ? 1 : 2;
-    const int p1 = st_pair_of(min(m, o1), max(m, o1)), p2 = st_pair_of(min(m, o2), max(m, o2));
-    const float* dg1 = p.adj_diag + (i64)p1 * p.N + off;
-    const float* dg2 = p.adj_diag + (i64)p2 * p.N + off;
-    const float4* x1 = reinterpret_cast<const float4*>(p.x + ((i64)o1 * p.N + off) * ST_G);
-    const float4* x2 = reinterpret_cast<const float4*>(p.x + ((i64)o2 * p.N + off) * ST_G);
-    float4* yb = reinterpret_cast<float4*>(p.y + ((i64)m * p.N + off) * ST_G);
-    const float4* tile = reinterpret_cast<const float4*>(rawz);
-    const int total = L * (ST_G / 4);
-    constexpr int EB = 5;                                     // 15 independent 128-bit loads in flight per thread
+    float4* tile = reinterpret_cast<float4*>(rawz);
 #pragma unroll 1
     for (int base = tid; base < total; base += EB * ST_CONV) {
-      float4 a1[EB], a2[EB], t[EB];
-      float d1[EB], d2[EB];
+      if (base != tid) {                                      // later batches: loads issued here
 #pragma unroll
-      for (int u = 0; u < EB; u++) {
-        const int i = base + u * ST_CONV;
-        if (i < total) {
-          const int r = i / (ST_G / 4);
-          a1[u] = __ldg(x1 + i);
-          a2[u] = __ldg(x2 + i);
-          d1[u] = __ldg(dg1 + r);
-          d2[u] = __ldg(dg2 + r);
-          t[u] = tile[i];
+        for (int u = 0; u < EB; u++) {
+          const int i = base + u * ST_CONV;
+          if (i < total) {
+            a1[u] = __ldg(x1 + i);
+            a2[u] = __ldg(x2 + i);
+          }
         }
       }
 #pragma unroll
       for (int u = 0; u < EB; u++) {
         const int i = base + u * ST_CONV;
-        if (i < total)
-          yb[i] = make_float4(t[u].x + d1[u] * a1[u].x + d2[u] * a2[u].x, t[u].y + d1[u] * a1[u].y + d2[u] * a2[u].y,
-                              t[u].z + d1[u] * a1[u].z + d2[u] * a2[u].z, t[u].w + d1[u] * a1[u].w + d2[u] * a2[u].w);
+        if (i < total) {
+          const int r = i / (ST_G / 4);
+          const float e1 = dsm[0][r], e2 = dsm[1][r];
+          const float4 t = tile[i];
+          tile[i] = make_float4(t.x + e1 * a1[u].x + e2 * a2[u].x, t.y + e1 * a1[u].y + e2 * a2[u].y,
+                                t.z + e1 * a1[u].z + e2 * a2[u].z, t.w + e1 * a1[u].w + e2 * a2[u].w);
+        }
       }
     }
+  }
+  umma::fence_proxy_async_smem();                             // tile writes -> visible to the bulk-copy engine
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (tid == 0 && L > 0) {
+    // the block's output rows are one contiguous, 16-byte aligned run of L * 400 bytes
+    float* yb = p.y + ((i64)m * p.N + off) * ST_G;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(yb), "r"(umma::smem_u32(rawz)), "r"((uint32_t)L * ST_G * 4) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
   ST_STAMP();                                                 // stored
   if (dbg_on) p.dbg[63] = dbg_n;

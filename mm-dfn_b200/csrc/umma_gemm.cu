@@ -348,10 +348,40 @@ __global__ void __launch_bounds__(UG_ALL_THREADS, BN <= 128 ? 2 : 1) umma_gemm_k
   const bool c_vec = (p.splits <= 1) && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
   constexpr int HALF = ((BN / 2 + 15) / 16) * 16;        // warps 0-3: columns [0, HALF), warps 4-7: [HALF, BN)
   const int cb_begin = (warp < 4) ? 0 : HALF, cb_end = (warp < 4) ? HALF : BN;
+  // beta != 0: this thread's 16 old C values of a column chunk are fetched with four 128-bit loads one chunk AHEAD of
+  // their use (row-per-lane addressing makes every load touch 32 lines: issued early and wide, their latency hides
+  // behind the TMEM reads; scalar loads at the point of use doubled the kernel's duration)
+  const bool c_old = (p.beta != 0.f) && (p.splits <= 1) && (row < p.M);
+  float4 cold[4];
+  auto fetch_c = [&](int cb) {
+    if (!c_old || cb >= cb_end || n0 + cb >= p.N) return;
+    const float* crow = p.C + (i64)row * p.ldc + n0 + cb;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; q4++) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int n = n0 + cb + 4 * q4;
+      if (c_vec && n + 3 < p.N) {
+        t = *reinterpret_cast<const float4*>(crow + 4 * q4);
+      } else {
+        if (n < p.N) t.x = crow[4 * q4];
+        if (n + 1 < p.N) t.y = crow[4 * q4 + 1];
+        if (n + 2 < p.N) t.z = crow[4 * q4 + 2];
+        if (n + 3 < p.N) t.w = crow[4 * q4 + 3];
+      }
+      cold[q4] = t;
+    }
+  };
+  fetch_c(cb_begin);
 #pragma unroll 1
   for (int cb = cb_begin; cb < cb_end; cb += 16) {
     if (n0 + cb >= p.N) break;                      // warp-uniform
     float v[16];
+    float cprev[16];
+#pragma unroll
+    for (int q4 = 0; q4 < 4; q4++) {
+      cprev[4 * q4] = cold[q4].x; cprev[4 * q4 + 1] = cold[q4].y; cprev[4 * q4 + 2] = cold[q4].z; cprev[4 * q4 + 3] = cold[q4].w;
+    }
+    fetch_c(cb + 16);
     if (nchunks > 0) {
       float w[16];
       umma::tmem_ld16(taddr + cb, v);
@@ -389,7 +419,7 @@ __global__ void __launch_bounds__(UG_ALL_THREADS, BN <= 128 ? 2 : 1) umma_gemm_k
         const int n = n0 + cb + q4 + q;
         float t = p.alpha * v[q4 + q];
         if (n < p.N) {
-          if (p.beta != 0.f) t = fmaf(p.beta, crow[q4 + q], t);
+          if (p.beta != 0.f) t = fmaf(p.beta, cprev[q4 + q], t);
           if (p.bias) t += p.bias[n];
         }
         if (p.act == 1) t = fmaxf(t, 0.f);
