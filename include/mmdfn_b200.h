@@ -57,6 +57,10 @@ int mmdfn_umma_probe(float* out, int N, int lbo, int sbo, int mn_major, int prob
 /* out[n] = beta*out[n] + sum_m A[m*lda+n]   (bias gradients) */
 int mmdfn_colsum(int M, int N, const float* A, long long lda, float beta, float* out, void* stream);
 
+/* Sequences per CTA of the recurrence kernels launched by the NEXT mmdfn_bigru2_fwd / _bwd calls: 2, 3, 4 or 8;
+ * 0 (default) = chosen from the sequence count.  Lets the caller size two encoders that run concurrently on two
+ * streams so that both fit in one wave of CTAs.  Host-side setting read at enqueue time (not stream-ordered). */
+int mmdfn_gru_set_tile(int nb);
 /* ---- k2: nn.GRU(200,100,num_layers=2,bidirectional=True), no packing, h0 = 0 -------------------
  * code/model.py:866 (lstm_l), :868 (rnn_parties); forward calls :1132, :1082, :1113, :1146.
  * x: (rows, 200) row table.  rowmap == NULL: rows == T*nseq and slot (t,s) reads row t*nseq+s.

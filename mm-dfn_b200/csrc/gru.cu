@@ -78,21 +78,35 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(GruFwdArgs p) {
       xn[b] = gate_of(rown[b]);          // consumed at the top of the next step
       rown[b] = row_of(step + 2, b);
     }
-    float2 acc2[NB];
+    // NACC independent accumulator pairs per sequence: with one, the 50 dependent FFMA2 of a sequence form a single
+    // latency chain (the compiler schedules sequence after sequence), which was the whole step time (~1040 cycles per
+    // sequence); short interleaved chains make the mat-vec issue-bound instead
+    constexpr int NACC = NB <= 2 ? 4 : 2;
+    float2 acc2[NB][NACC];
 #pragma unroll
-    for (int b = 0; b < NB; b++) acc2[b] = make_float2(bh, 0.f);
+    for (int b = 0; b < NB; b++) {
+      acc2[b][0] = make_float2(bh, 0.f);
+#pragma unroll
+      for (int a = 1; a < NACC; a++) acc2[b][a] = make_float2(0.f, 0.f);
+    }
 #pragma unroll
     for (int k = 0; k < GH; k += 4) {
 #pragma unroll
       for (int b = 0; b < NB; b++) {
         const float4 h4 = *reinterpret_cast<const float4*>(&hs[b][k]);
-        acc2[b] = __ffma2_rn(w2[k / 2], make_float2(h4.x, h4.y), acc2[b]);
-        acc2[b] = __ffma2_rn(w2[k / 2 + 1], make_float2(h4.z, h4.w), acc2[b]);
+        float2& a2 = acc2[b][(k / 4) % NACC];
+        a2 = __ffma2_rn(w2[k / 2], make_float2(h4.x, h4.y), a2);
+        a2 = __ffma2_rn(w2[k / 2 + 1], make_float2(h4.z, h4.w), a2);
       }
     }
     float acc[NB];
 #pragma unroll
-    for (int b = 0; b < NB; b++) acc[b] = acc2[b].x + acc2[b].y;
+    for (int b = 0; b < NB; b++) {
+      float2 t = acc2[b][0];
+#pragma unroll
+      for (int a = 1; a < NACC; a++) { t.x += acc2[b][a].x; t.y += acc2[b][a].y; }
+      acc[b] = t.x + t.y;
+    }
     if (tid < G3) {
 #pragma unroll
       for (int b = 0; b < NB; b++) {
@@ -297,11 +311,17 @@ __global__ void mask_mul_kernel(const float* __restrict__ x, const unsigned char
   if (i < n) y[i] = m[i] ? x[i] * scale : 0.f;
 }
 
-// Sequences per CTA.  The recurrence is issue-bound per CTA (100 FMAs per sequence per thread and step), so fewer
-// sequences per CTA shorten every step as long as the CTAs still fit in one wave; the text encoder and the party
-// encoder run concurrently on two streams, so a launch takes at most ~2/3 of the SMs (100 CTAs) before it widens its
-// tiles: text (32 sequences) -> NB 2 / 32 CTAs, party (192) -> NB 4 / 96 CTAs, more than 400 sequences -> NB 8.
+// Sequences per CTA (NB).  Measured with clock64 stamps (profiles/r01_gru_phase_stamps_s2.log): a step costs about
+// 260 + 750 NB cycles of mat-vec (bound by shared-memory wavefronts: every warp re-reads the NB hidden vectors as
+// broadcast 128-bit loads) plus 600 cycles per pass of the pointwise phase (320 items per pass), so fewer sequences
+// per CTA shorten every step as long as all CTAs are co-resident.  The text encoder and the party encoder run
+// concurrently on two streams; the model sets the tile for each launch through mmdfn_gru_set_tile so that both fit in
+// one wave (bench shard: text NB 4 = 16 CTAs, party NB 3 = 128 CTAs).  Automatic choice (tile 0): a launch takes at
+// most ~2/3 of the SMs before it widens its tiles.
+static int g_gru_tile = 0;
+
 static int gru_pick_nb(int nseq) {
+  if (g_gru_tile == 2 || g_gru_tile == 3 || g_gru_tile == 4 || g_gru_tile == 8) return g_gru_tile;
   if (2 * ceil_div(nseq, 2) <= 100) return 2;
   if (2 * ceil_div(nseq, 4) <= 100) return 4;
   return (i64)ceil_div(nseq, 8) * 2 >= 148 ? 8 : 4;
@@ -314,6 +334,8 @@ static int launch_gru_fwd(const GruFwdArgs& a, cudaStream_t st) {
     gru_fwd_kernel<8><<<dim3(ceil_div(a.nseq, 8), 2), GRU_THREADS, 0, st>>>(a);
   } else if (nb == 4) {
     gru_fwd_kernel<4><<<dim3(ceil_div(a.nseq, 4), 2), GRU_THREADS, 0, st>>>(a);
+  } else if (nb == 3) {
+    gru_fwd_kernel<3><<<dim3(ceil_div(a.nseq, 3), 2), GRU_THREADS, 0, st>>>(a);
   } else {
     gru_fwd_kernel<2><<<dim3(ceil_div(a.nseq, 2), 2), GRU_THREADS, 0, st>>>(a);
   }
@@ -328,6 +350,8 @@ static int launch_gru_bwd(const GruBwdArgs& a, cudaStream_t st) {
     gru_bwd_kernel<8><<<dim3(ceil_div(a.nseq, 8), 2), GRU_THREADS, 0, st>>>(a);
   } else if (nb == 4) {
     gru_bwd_kernel<4><<<dim3(ceil_div(a.nseq, 4), 2), GRU_THREADS, 0, st>>>(a);
+  } else if (nb == 3) {
+    gru_bwd_kernel<3><<<dim3(ceil_div(a.nseq, 3), 2), GRU_THREADS, 0, st>>>(a);
   } else {
     gru_bwd_kernel<2><<<dim3(ceil_div(a.nseq, 2), 2), GRU_THREADS, 0, st>>>(a);
   }
@@ -338,6 +362,12 @@ static int launch_gru_bwd(const GruBwdArgs& a, cudaStream_t st) {
 }  // namespace mmdfn
 
 using namespace mmdfn;
+
+extern "C" int mmdfn_gru_set_tile(int nb) {
+  if (nb != 0 && nb != 2 && nb != 3 && nb != 4 && nb != 8) return MMDFN_EINVAL;
+  g_gru_tile = nb;
+  return 0;
+}
 
 // Weight pointer table order (16 entries), matching nn.GRU's state_dict names:
 //   [0..3]  weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0

@@ -393,9 +393,10 @@ class DialogueGNNModel(nn.Module):
         # few-CTA, latency-bound recurrences, so it runs on a side stream (autograd replays the same stream in backward).
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev) if self.use_crn_speaker else None
+        tile_l, tile_p = ops.plan_gru_tiles(T, B, 3 * B * S) if side is not None else (0, 0)
         if side is not None:
             side.wait_stream(main)
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(side), ops.gru_tile(tile_l):
                 E_l = ops.BiGRU2Fn.apply(Utab[2].reshape(T * B, 200), None, T, B, m_l, scale, *self._gru_weights(self.lstm_l))
         else:
             E_l = ops.BiGRU2Fn.apply(Utab[2].reshape(T * B, 200), None, T, B, m_l, scale, *self._gru_weights(self.lstm_l))
@@ -405,8 +406,9 @@ class DialogueGNNModel(nn.Module):
             pos, _cnt, sel, rowmap = ops.spk_partition(qmask)
             nseq = 3 * B * S
             m_p = ops.make_mask((T, nseq, 200), p, dev) if train_drop else mk.get("gru_p")
-            Q = ops.BiGRU2Fn.apply(Utab.reshape(3 * T * B, 200), rowmap, T, nseq, m_p, scale,
-                                   *self._gru_weights(self.rnn_parties))
+            with ops.gru_tile(tile_p):
+                Q = ops.BiGRU2Fn.apply(Utab.reshape(3 * T * B, 200), rowmap, T, nseq, m_p, scale,
+                                       *self._gru_weights(self.rnn_parties))
         if side is not None:
             main.wait_stream(side)
             E_l.record_stream(main)

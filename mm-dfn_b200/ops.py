@@ -162,6 +162,45 @@ GRU_KEYS = [f"{k}_l{l}{sfx}" for l in (0, 1) for sfx in ("", "_reverse")
 _GRU_GRAD_ORDER = [0, 4, 1, 5, 2, 3, 6, 7, 8, 12, 9, 13, 10, 11, 14, 15]
 
 
+_GRU_TILE = [0]      # sequences per CTA for the BiGRU2Fn calls issued inside a `gru_tile(nb)` block (0 = library default)
+
+
+class gru_tile:
+    """Context manager: recurrence tile (sequences per CTA: 2, 3, 4, 8; 0 = automatic) for the BiGRU2Fn.apply calls in
+    the block, remembered by each call for its backward.  Used by the model to fit two concurrently running encoders
+    into one wave of CTAs (mmdfn_gru_set_tile)."""
+
+    def __init__(self, nb):
+        self.nb, self.prev = int(nb), 0
+
+    def __enter__(self):
+        self.prev, _GRU_TILE[0] = _GRU_TILE[0], self.nb
+
+    def __exit__(self, *exc):
+        _GRU_TILE[0] = self.prev
+
+
+def plan_gru_tiles(T, n_a, n_b, sms=148):
+    """Tiles (nb_a, nb_b) for two 2-layer BiGRU encoders with n_a and n_b sequences that run concurrently: minimise the
+    longer of the two, subject to both grids (2 * ceil(n / nb) CTAs each) being co-resident.  Per-step cost model from
+    clock64 stamps on B200 (profiles/r01_gru_phase_stamps_s2.log): 260 + 750 nb cycles of mat-vec + 600 per pointwise
+    pass of 320 items; the hoisted input GEMMs are charged at 40 TFLOP/s.  Returns (0, 0) if nothing fits."""
+    def enc_us(n, nb, rows_l0):
+        step = 260 + 750 * nb + 600 * -(-(nb * 100) // 320)
+        gemm = 2.0 * 600 * 200 * (rows_l0 + T * n) / 40e12 * 1e6
+        return gemm + 2 * T * step / 1965.0
+    best, pick = None, (0, 0)
+    for na in (2, 3, 4, 8):
+        for nb in (2, 3, 4, 8):
+            if 2 * -(-n_a // na) + 2 * -(-n_b // nb) > sms:
+                continue
+            ta, tb = enc_us(n_a, na, T * n_a), enc_us(n_b, nb, T * n_b / 2)
+            key = (max(ta, tb), ta + tb)
+            if best is None or key < best:
+                best, pick = key, (na, nb)
+    return pick
+
+
 class BiGRU2Fn(torch.autograd.Function):
     """x (rows,200) [+ rowmap (T,nseq) gather] -> y (T,nseq,200).  16 weights in GRU_KEYS order."""
 
@@ -173,8 +212,13 @@ class BiGRU2Fn(torch.autograd.Function):
         y = _empty((T, nseq, 200), x.device)
         ws = _empty((query("mmdfn_bigru2_ws_floats", T, nseq, rows),), x.device)
         tab = ptr_table(w)
-        call("mmdfn_bigru2_fwd", T, nseq, rows, ptr(x), ptr(rowmap, torch.int32), tab, ptr(mask, U8),
-             float(mask_scale), ptr(y), ptr(ws), stream())
+        ctx.tile = _GRU_TILE[0]
+        call("mmdfn_gru_set_tile", ctx.tile)
+        try:
+            call("mmdfn_bigru2_fwd", T, nseq, rows, ptr(x), ptr(rowmap, torch.int32), tab, ptr(mask, U8),
+                 float(mask_scale), ptr(y), ptr(ws), stream())
+        finally:
+            call("mmdfn_gru_set_tile", 0)
         ctx.save_for_backward(x, y, ws, *w)
         ctx.rowmap, ctx.mask, ctx.mask_scale, ctx.T, ctx.nseq = rowmap, mask, float(mask_scale), T, nseq
         return y
@@ -196,8 +240,12 @@ class BiGRU2Fn(torch.autograd.Function):
             off += n
         wsb = _empty((query("mmdfn_bigru2_bwd_ws_floats", T, nseq, rows),), x.device)
         tab, dtab = ptr_table(w), ptr_table(dw)
-        call("mmdfn_bigru2_bwd", T, nseq, rows, ptr(x), ptr(ctx.rowmap, torch.int32), tab, ptr(ctx.mask, U8),
-             ctx.mask_scale, ptr(y), ptr(dy), ptr(ws), ptr(dx), 0, dtab, 1, ptr(wsb), stream())
+        call("mmdfn_gru_set_tile", ctx.tile)
+        try:
+            call("mmdfn_bigru2_bwd", T, nseq, rows, ptr(x), ptr(ctx.rowmap, torch.int32), tab, ptr(ctx.mask, U8),
+                 ctx.mask_scale, ptr(y), ptr(dy), ptr(ws), ptr(dx), 0, dtab, 1, ptr(wsb), stream())
+        finally:
+            call("mmdfn_gru_set_tile", 0)
         return (dx, None, None, None, None, None, *dw)
 
 
