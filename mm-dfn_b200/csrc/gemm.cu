@@ -100,12 +100,15 @@ int gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64
   if (2.0 * (double)M * (double)N * (double)K >= 2.0e8)
     return umma_gemm(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act, st);
   GemmArgs p{A, lda, B, ldb, C, ldc, bias, M, N, K, alpha, beta, act, 1};
-  const bool big = (i64)ceil_div(M, 128) * ceil_div(N, 64) >= 148;
+  // 128 x 64 tiles (8 x 4 per thread) only when even they give every SM several CTAs; otherwise 64 x 64 tiles: twice the
+  // CTAs and warps per SM (the 128 x 64 kernel ran one 8-warp CTA per SM at 12 % occupancy and 40 % issue utilisation
+  // on the 9600 x 100 x 100 products of the graph layers)
+  const bool big = (i64)ceil_div(M, 128) * ceil_div(N, 64) >= 3 * 148;
   const i64 tiles = big ? (i64)ceil_div(M, 128) * ceil_div(N, 64) : (i64)ceil_div(M, 64) * ceil_div(N, 64);
   // split the contraction when the output is too small to fill 148 SMs (weight gradients)
   if (tiles < 296 && K >= 1024 && bias == nullptr && act == 0) {
     i64 s = ceil_div64(592, tiles);
-    const i64 smax = ceil_div(K, 256);
+    const i64 smax = ceil_div(K, 128);
     p.splits = (int)(s < smax ? s : smax);
     if (p.splits < 1) p.splits = 1;
   }
