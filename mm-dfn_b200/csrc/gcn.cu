@@ -180,7 +180,8 @@ extern "C" int mmdfn_gcn_stack_fwd(int B, int N, int Lmax, const int* dia_off, c
     const float* agg_in = zl;
     if (reason_flag) {
       MMDFN_TRY(gemm(false, true, (int)n3, 4 * GG, GG, 1.f, zl, GG, w_ih, GG, 0.f, pre, 4 * GG, b_ih, 0, st));
-      MMDFN_TRY(gemm(false, true, (int)n3, 4 * GG, GG, 1.f, hl, GG, w_hh, GG, 1.f, pre, 4 * GG, b_hh, 0, st));
+      // layer 0 starts from h = 0: its recurrent product is zero, only b_hh is added (a K = 0 call of the same entry point)
+      MMDFN_TRY(gemm(false, true, (int)n3, 4 * GG, l == 0 ? 0 : GG, 1.f, hl, GG, w_hh, GG, 1.f, pre, 4 * GG, b_hh, 0, st));
       lstm_fwd_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3, pre, cl, gates, c, h);
       MMDFN_LAUNCH_CHECK();
       agg_in = h;
@@ -293,7 +294,11 @@ extern "C" int mmdfn_gcn_stack_bwd(int B, int N, int Lmax, const int* dia_off, c
     if (l > 0) MMDFN_TRY(gemm(false, false, (int)n3, GG, 4 * GG, 1.f, dgates, 4 * GG, w_hh, GG, 0.f, dhc, GG, nullptr, 0, st));
     const float beta = (first_rnn && !grads_zeroed) ? 0.f : 1.f;
     MMDFN_TRY(gemm(true, false, 4 * GG, GG, (int)n3, 1.f, dgates, 4 * GG, zprev, GG, beta, dw_ih, GG, nullptr, 0, st));
-    MMDFN_TRY(gemm(true, false, 4 * GG, GG, (int)n3, 1.f, dgates, 4 * GG, hprev, GG, beta, dw_hh, GG, nullptr, 0, st));
+    if (l > 0) {
+      MMDFN_TRY(gemm(true, false, 4 * GG, GG, (int)n3, 1.f, dgates, 4 * GG, hprev, GG, beta, dw_hh, GG, nullptr, 0, st));
+    } else if (beta == 0.f) {
+      MMDFN_TRY(fill_zero(dw_hh, (size_t)4 * GG * GG * sizeof(float), st));      // h_{-1} = 0: no contribution from layer 0
+    }
     MMDFN_TRY(colsum((int)n3, 4 * GG, dgates, 4 * GG, beta, db_ih, st));
     first_rnn = false;
     have_carry = true;

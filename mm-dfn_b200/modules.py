@@ -385,7 +385,19 @@ class DialogueGNNModel(nn.Module):
         train_drop = self.training and p > 0 and masks is None
         scale = 1.0 / (1.0 - p) if (train_drop or masks is not None) else 1.0
         mk = masks or {}
-        m_l = ops.make_mask((T, B, 200), p, dev) if train_drop else mk.get("gru_l")
+        # every dropout keep-mask of the step comes from one launch (same counter stream, same bits as separate draws):
+        # text GRU, party GRU, head, and -- when the graph stack uses the same rate on the GDF path -- its three masks
+        nseq_p = 3 * B * S if self.use_crn_speaker else 0
+        gcn = self.graph_model.graph_net if self.graph_type != 'relation' else None
+        pool_gcn = (train_drop and gcn is not None and gcn.training and float(gcn.dropout) == p)
+        pooled = None
+        if train_drop:
+            shapes = [(T, B, 200), (T, nseq_p, 200), (geom.N, 900)]
+            if pool_gcn:
+                Kc, n3 = len(gcn.convs), 3 * geom.N
+                shapes += [(n3, 200), (n3, 100), (Kc, n3, 100)]
+            pooled = ops.make_masks(shapes, p, dev)
+        m_l = pooled[0] if train_drop else mk.get("gru_l")
         # k1: the three projections into one stacked table (a, v, l)
         Utab = ops.Proj3Fn.apply(U_a, U_v, U, self.linear_a.weight, self.linear_a.bias, self.linear_v.weight,
                                  self.linear_v.bias, self.linear_l.weight, self.linear_l.bias)
@@ -405,7 +417,7 @@ class DialogueGNNModel(nn.Module):
             # k3: shared speaker-party BiGRU over all (modality, dialogue, speaker) sequences at once
             pos, _cnt, sel, rowmap = ops.spk_partition(qmask)
             nseq = 3 * B * S
-            m_p = ops.make_mask((T, nseq, 200), p, dev) if train_drop else mk.get("gru_p")
+            m_p = pooled[1] if train_drop else mk.get("gru_p")
             with ops.gru_tile(tile_p):
                 Q = ops.BiGRU2Fn.apply(Utab.reshape(3 * T * B, 200), rowmap, T, nseq, m_p, scale,
                                        *self._gru_weights(self.rnn_parties))
@@ -414,10 +426,12 @@ class DialogueGNNModel(nn.Module):
             E_l.record_stream(main)
         # k3/k4: scatter + speaker-weight combine + ragged pack, written as the stacked graph input
         X = ops.PartyPackFn.apply(Utab, E_l, Q, geom, sel, pos, S, tuple(self.speaker_weights))
-        m_h = ops.make_mask((geom.N, 900), p, dev) if train_drop else mk.get("head")
+        m_h = pooled[2] if train_drop else mk.get("head")
         if self.graph_type == 'relation':
             return self._forward_relation(X, E_l, qmask, geom, seq_lengths, umask, m_h, scale)
         gm = mk.get("gcn") if masks is not None else None
+        if pool_gcn:
+            gm = {"x": pooled[3], "h0": pooled[4], "layers": pooled[5] if len(gcn.convs) > 0 else None}
         F_ = self.graph_model.forward_stacked(X, geom, gm)
         log_prob = ops.HeadFn.apply(F_, geom.N, m_h, scale, self.smax_fc.weight, self.smax_fc.bias)
         return log_prob, None, None, None, None

@@ -64,6 +64,28 @@ def make_mask(shape, p, device):
     return m
 
 
+def make_masks(shapes, p, device):
+    """Several keep-masks with ONE launch: one uint8 buffer, views in request order.  Element i of the concatenation
+    uses counter base + i, so the bits equal those of consecutive make_mask calls in the same order."""
+    sizes = []
+    for shape in shapes:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        sizes.append(n)
+    total = sum(sizes)
+    buf = _empty((total,), device, U8)
+    seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    if total:
+        call("mmdfn_dropout_mask", total, float(p), seed, _mask_counter[0], ptr(buf, U8), stream())
+    _mask_counter[0] = (_mask_counter[0] + total) & 0xFFFFFFFFFFFFFFFF
+    out, off = [], 0
+    for shape, n in zip(shapes, sizes):
+        out.append(buf[off:off + n].view(*shape))
+        off += n
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # k1: projections
 # ---------------------------------------------------------------------------------------------
