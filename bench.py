@@ -216,11 +216,12 @@ def roofline_graph_conv(dev, n_dialogues=DIALOGUES_PER_GPU):
     us = e0.elapsed_time(e1) * 1e3 / reps
     peak, how = measured_peak_gbs()
     achieved = alg_bytes / (us * 1e-6) / 1e9
-    return {"kernel": "adj_spmm_kernel (k6 graph-conv message aggregate hi = A_hat z, fp32)", "bound": "hbm",
+    return {"kernel": "adj_spmm_tc_kernel (k6 graph-conv message aggregate hi = A_hat z; tcgen05 3xTF32, fp32-level accuracy)", "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel inside a training step
-            # (ncu --set full, profiles/r01_ncu_adj_spmm100_final.csv; z and A_hat are partly L2-resident there)
-            "traffic": 7767296 if n_dialogues == DIALOGUES_PER_GPU else None,
+            # (ncu --set full, profiles/r01_ncu_adj_spmm_tc_s2.csv: 7.76 MB read, 0 written -- z is partly L2-resident
+            # and the 3.84 MB of output stay in L2 for the consumer)
+            "traffic": 7761152 if n_dialogues == DIALOGUES_PER_GPU else None,
             "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us, "peak_source": how,
             "note": "launch covers one GCN layer of the %dx100 shard; operands rotated over %d copies (> L2)" % (n_dialogues, copies)}
 
@@ -244,6 +245,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured whole-step CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args, real_stdout)
@@ -291,10 +293,17 @@ def main():
     h2d_bytes = sum(x.numel() * x.element_size() for x in host[0])
 
     res_events = []
+    use_graph = [False]
+
+    def run_step(t, a, v, q, u, lab):
+        """the public API call of one training step: FlatAdamTrainer.replay (captured CUDA graph) or .step (eager)"""
+        if use_graph[0]:
+            return trainer.replay(t, q, u, a, v, lab)
+        return trainer.step(t, q, u, lengths, a, v, lab, n_global)
 
     def step_resident(i):
         t, a, v, q, u, lab = resident[i % N_BATCHES]
-        out = trainer.step(t, q, u, lengths, a, v, lab, n_global)
+        out = run_step(t, a, v, q, u, lab)
         # keep the host at most two steps ahead of the device: unbounded run-ahead makes the caching allocator grow
         # (blocks used on the side stream cannot be recycled before their events complete) and a cudaMalloc in the
         # timed region stalls the queue -- measured as 3.3 -> 3.7 .. 6.7 ms/step run-to-run noise
@@ -327,7 +336,7 @@ def main():
         torch.cuda.current_stream(dev).wait_event(ev)
         for x in (t, a, v, q, u, lab):
             x.record_stream(torch.cuda.current_stream(dev))
-        loss = trainer.step(t, q, u, lengths, a, v, lab, n_global)
+        loss = run_step(t, a, v, q, u, lab)
         # D2H read of the step's result, every step: an asynchronous 4-byte copy into pinned memory behind the step's
         # kernels; the host consumes it one step later (and the last one before the timed region closes), so the read
         # does not drain the launch queue -- what a training loop that logs the loss does
@@ -374,6 +383,26 @@ def main():
 
     for i in range(W):
         step_resident(i)
+    launches_per_step = None
+    graph_note = "eager launches (--no-graph)"
+    if not args.no_graph:
+        # whole-step CUDA graph (FlatAdamTrainer.capture): one launch per step; falls back to eager launches if the
+        # capture fails, and says so in the JSON line
+        try:
+            torch.cuda.synchronize()
+            res_events.clear()
+            l0 = query("mmdfn_launch_count")
+            t, a, v, q, u, lab = resident[0]
+            trainer.capture(t, q, u, lengths, a, v, lab, n_global, warmup=0)
+            launches_per_step = query("mmdfn_launch_count") - l0
+            use_graph[0] = True
+            graph_note = "whole step (fwd+bwd+all-reduce+Adam) replayed as one captured CUDA graph"
+        except Exception as e:  # pragma: no cover
+            use_graph[0] = False
+            graph_note = "eager launches (graph capture failed: %r)" % (e,)
+            print("graph capture failed, running eager:", repr(e), file=sys.stderr)
+        for i in range(W):
+            step_resident(i)
     for i in range(2):
         step_e2e(i)
     drain_losses()
@@ -383,6 +412,8 @@ def main():
     launches0 = query("mmdfn_launch_count")
     sec, wall = timed(step_resident, K)
     launches = query("mmdfn_launch_count") - launches0
+    if use_graph[0]:
+        launches = launches_per_step * K          # kernels inside the replayed graph (counted once at capture)
     inflight.clear()
     losses_seen.clear()
     sec_e2e, _ = timed(step_e2e, K, finish=drain_losses)
@@ -399,6 +430,7 @@ def main():
                         "note": "inputs pinned-host -> device every step on a copy stream one batch ahead; the loss is copied D2H "
                                 "every step (async, pinned) and consumed by the host one step later, all %d inside the timed region" % K},
                 "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall}
+        line["config"]["launch_mode"] = graph_note
         try:
             line["roofline"] = roofline_graph_conv(dev)
             big = roofline_graph_conv(dev, 256)          # BASELINE config 4 on one GPU (256 x 100 utterances): steady-state view

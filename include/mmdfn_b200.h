@@ -214,6 +214,17 @@ int mmdfn_dropout_mask(long long n, float p, unsigned long long seed, unsigned l
 int mmdfn_adam_step(long long n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                     void* stream);
+/* CUDA-graph friendly variants: everything that changes from step to step is read from a device-resident state
+ * (2 x uint64: [0] = optimizer steps taken, [1] = two floats {1 - beta1^t, sqrt(1 - beta2^t)} of the step in flight).
+ * mmdfn_step_advance increments [0] and refreshes [1] (call it once per step, before mmdfn_adam_step_dev);
+ * mmdfn_dropout_mask_dev draws with counter base offset + state[0] * per_step. */
+int mmdfn_step_advance(unsigned long long* state, float beta1, float beta2, void* stream);
+int mmdfn_dropout_mask_dev(long long n, float p, unsigned long long seed, const unsigned long long* state,
+                           unsigned long long per_step, unsigned long long offset, unsigned char* mask,
+                           void* stream);
+int mmdfn_adam_step_dev(long long n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, const unsigned long long* state,
+                        float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

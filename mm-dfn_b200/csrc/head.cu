@@ -117,6 +117,49 @@ __global__ void dropout_mask_kernel(i64 n, float p, unsigned long long seed, uns
   mask[idx] = u >= p ? 1 : 0;
 }
 
+// Device-resident step state for CUDA-graph replays (nothing that changes from step to step may be a kernel
+// argument there): state[0] = number of optimizer steps taken, state[1] = two floats {1 - beta1^t, sqrt(1 - beta2^t)}
+// for the step that is being taken.
+__global__ void step_advance_kernel(unsigned long long* state, float beta1, float beta2) {
+  const unsigned long long t = state[0] + 1ull;
+  state[0] = t;
+  float* bc = reinterpret_cast<float*>(state + 1);
+  bc[0] = 1.0f - powf(beta1, (float)t);
+  bc[1] = sqrtf(1.0f - powf(beta2, (float)t));
+}
+
+// keep mask whose counter base advances with the device-resident step index: offset + state[0] * per_step
+__global__ void dropout_mask_dev_kernel(i64 n, float p, unsigned long long seed, const unsigned long long* __restrict__ state,
+                                        unsigned long long per_step, unsigned long long offset,
+                                        unsigned char* __restrict__ mask) {
+  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const unsigned long long base = offset + state[0] * per_step;
+  unsigned long long z = seed * 0x9E3779B97F4A7C15ull + (base + (unsigned long long)idx) * 0xD1342543DE82EF95ull;
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);   // [0,1)
+  mask[idx] = u >= p ? 1 : 0;
+}
+
+__global__ void adam_dev_kernel(i64 n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, float lr, float beta1, float beta2, float eps, float wd,
+                                const unsigned long long* __restrict__ state, float gscale) {
+  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const float* bc = reinterpret_cast<const float*>(state + 1);
+  const float bc1 = bc[0], bc2_sqrt = bc[1];
+  const float w = p[idx];
+  const float gr = fmaf(wd, w, g[idx] * gscale);
+  const float mm = beta1 * m[idx] + (1.f - beta1) * gr;
+  const float vv = beta2 * v[idx] + (1.f - beta2) * gr * gr;
+  m[idx] = mm;
+  v[idx] = vv;
+  const float denom = sqrtf(vv) / bc2_sqrt + eps;
+  p[idx] = w - (lr / bc1) * (mm / denom);
+}
+
 // Adam with L2 folded into the gradient (torch.optim.Adam weight_decay semantics), grads pre-scaled by gscale
 __global__ void adam_kernel(i64 n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, float lr, float beta1, float beta2, float eps, float wd,
@@ -221,6 +264,35 @@ extern "C" int mmdfn_adam_step(long long n, float* param, const float* grad, flo
   const float bc2 = sqrtf(1.0f - powf(beta2, (float)step));
   adam_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2,
                                                                       eps, weight_decay, bc1, bc2, grad_scale);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- CUDA-graph friendly variants: the step index lives on the device (state: 2 x uint64, see step_advance_kernel) ----
+extern "C" int mmdfn_step_advance(unsigned long long* state, float beta1, float beta2, void* stream) {
+  if (!state) return MMDFN_ENULL;
+  step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, beta1, beta2);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmdfn_dropout_mask_dev(long long n, float p, unsigned long long seed, const unsigned long long* state,
+                                      unsigned long long per_step, unsigned long long offset, unsigned char* mask,
+                                      void* stream) {
+  if (!mask || !state) return MMDFN_ENULL;
+  if (n <= 0) return 0;
+  dropout_mask_dev_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(n, p, seed, state, per_step, offset, mask);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmdfn_adam_step_dev(long long n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                   float lr, float beta1, float beta2, float eps, float weight_decay,
+                                   const unsigned long long* state, float grad_scale, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !state) return MMDFN_ENULL;
+  if (n <= 0) return 0;
+  adam_dev_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(n, param, grad, exp_avg, exp_avg_sq, lr, beta1,
+                                                                          beta2, eps, weight_decay, state, grad_scale);
   MMDFN_LAUNCH_CHECK();
   return 0;
 }

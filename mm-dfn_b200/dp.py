@@ -59,6 +59,8 @@ class FlatAdamTrainer:
             off += n
         self.total = total
         self.step_count = 0
+        self._state = None            # device-resident step state (graph mode, see capture())
+        self._graph = None
         if self.world > 1:                                        # replicas start identical
             dist.broadcast(self.flat_p, src=0, group=self.pg)
 
@@ -76,8 +78,59 @@ class FlatAdamTrainer:
         torch._foreach_copy_(self.grad_views, [p.grad for p in self.params])   # one multi-tensor gather into the bucket
         if self.world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+        if self._state is not None:
+            # graph mode: the step index and Adam's bias corrections live on the device (captured launches cannot
+            # take per-step arguments)
+            call("mmdfn_step_advance", ptr(self._state, torch.int64), float(self.betas[0]), float(self.betas[1]), stream())
+            call("mmdfn_adam_step_dev", self.total, ptr(self.flat_p), ptr(self.flat_g), ptr(self.exp_avg),
+                 ptr(self.exp_avg_sq), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                 float(self.wd), ptr(self._state, torch.int64), 1.0, stream())
+            if not torch.cuda.is_current_stream_capturing():
+                self.step_count += 1
+            return loss.detach()
         self.step_count += 1
         call("mmdfn_adam_step", self.total, ptr(self.flat_p), ptr(self.flat_g), ptr(self.exp_avg), ptr(self.exp_avg_sq),
              float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd),
              self.step_count, 1.0, stream())
         return loss.detach()
+
+    # ---- whole-step CUDA graph -------------------------------------------------------------------------------------
+    def capture(self, textf, qmask, umask, lengths, acouf, visuf, label, n_global=None, warmup=1):
+        """Capture fwd + bwd + (all-reduce) + Adam for batches of exactly these shapes and lengths into ONE CUDA graph.
+        Afterwards `replay(textf, qmask, umask, acouf, visuf, label)` runs a step with a single launch: the ~130 kernel
+        launches and their inter-kernel gaps disappear from the host and shrink on the device.  Per-step quantities
+        (dropout counter, Adam step index / bias corrections) are read from a device-resident state, so replays draw fresh
+        masks and apply the right corrections.  The eager `step` keeps working for other shapes (it shares the state)."""
+        from . import ops
+        dev = self.flat_p.device
+        self._static = tuple(torch.empty_like(x) for x in (textf, qmask, umask, acouf, visuf, label))
+        for dst, src in zip(self._static, (textf, qmask, umask, acouf, visuf, label)):
+            dst.copy_(src)
+        self._lengths, self._n_global = [int(x) for x in lengths], n_global
+        self._state = torch.zeros(2, dtype=torch.int64, device=dev)
+        self._state[0] = self.step_count
+        ops.set_step_state(self._state)
+        t, q, u, a, v, lab = self._static
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                       # warm-up off the default stream, as graph capture requires
+            for _ in range(max(0, warmup)):      # real training steps on this batch (0 if eager steps ran before)
+                self.step(t, q, u, self._lengths, a, v, lab, n_global)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for p in self.params:
+            p.grad = None
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self.step(t, q, u, self._lengths, a, v, lab, n_global)
+        torch.cuda.synchronize(dev)
+        return self
+
+    def replay(self, textf, qmask, umask, acouf, visuf, label):
+        """One captured step on a new batch of the captured shapes; returns the (static) loss tensor."""
+        for dst, src in zip(self._static, (textf, qmask, umask, acouf, visuf, label)):
+            if src is not dst:
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        self.step_count += 1
+        return self._static_loss

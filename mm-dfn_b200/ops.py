@@ -54,14 +54,17 @@ _mask_counter = [0]
 
 
 def make_mask(shape, p, device):
-    n = 1
-    for s in shape:
-        n *= int(s)
-    m = _empty(shape, device, U8)
-    seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-    call("mmdfn_dropout_mask", n, float(p), seed, _mask_counter[0], ptr(m, U8), stream())
-    _mask_counter[0] = (_mask_counter[0] + n) & 0xFFFFFFFFFFFFFFFF
-    return m
+    return make_masks([tuple(shape)], p, device)[0]
+
+
+# CUDA-graph mode: device-resident step state (int64[2], see mmdfn_step_advance).  When set, make_masks draws with a
+# counter base that advances with the device-side step index, so every replay of a captured step gets fresh masks.
+_STEP_STATE = [None]
+
+
+def set_step_state(state):
+    """state: int64[2] CUDA tensor (or None to leave graph mode)."""
+    _STEP_STATE[0] = state
 
 
 def make_masks(shapes, p, device):
@@ -76,7 +79,12 @@ def make_masks(shapes, p, device):
     total = sum(sizes)
     buf = _empty((total,), device, U8)
     seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-    if total:
+    st = _STEP_STATE[0]
+    if total and st is not None:
+        # counter base = this call's offset + (steps taken so far) * 2^40: distinct per call and per replayed step
+        call("mmdfn_dropout_mask_dev", total, float(p), seed, ptr(st, torch.int64), 1 << 40, _mask_counter[0], ptr(buf, U8),
+             stream())
+    elif total:
         call("mmdfn_dropout_mask", total, float(p), seed, _mask_counter[0], ptr(buf, U8), stream())
     _mask_counter[0] = (_mask_counter[0] + total) & 0xFFFFFFFFFFFFFFFF
     out, off = [], 0

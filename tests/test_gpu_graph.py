@@ -1,0 +1,77 @@
+"""Whole-step CUDA graph (FlatAdamTrainer.capture / replay): replays must train exactly like eager steps, draw fresh
+dropout masks every replay and apply Adam's bias correction of the right step index (both live on the device)."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LENGTHS = [17, 9, 30, 12, 25, 8]
+
+
+def _build(dev, dropout):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import mmdfn_b200
+    import mmdfn_oracle as O
+    from helpers import model_shapes
+    m = mmdfn_b200.DialogueGNNModel("LSTM", 100, 150, 150, 100, 100, 100, 100, n_speakers=2, max_seq_len=200, window_past=10,
+                                    window_future=10, n_classes=6, dropout=dropout, graph_type="GDF", alpha=0.2, lamda=0.5,
+                                    D_m_v=48, D_m_a=64, modals="avl", att_type="concat_subsequently", Deep_GCN_nlayers=2,
+                                    use_speaker=False, reason_flag=True, use_crn_speaker=True, speaker_weights="3-0-1")
+    m.load_state_dict(O.formula_weights(model_shapes(100, 64, 48, 2, 6, 2)))
+    batches = [O.synthetic_batch(LENGTHS, 100, 64, 48, 2, 6, seed=s) for s in (2, 3, 4)]
+    return mmdfn_b200, m.to(dev).train(), [tuple(x.to(dev) for x in b) for b in batches]
+
+
+def _trainer(mm, model, lr=1e-3):
+    from mmdfn_b200.dp import FlatAdamTrainer
+    return FlatAdamTrainer(model, mm.FocalLoss(gamma=1.0), lr=lr, weight_decay=1e-4)
+
+
+@pytest.fixture(autouse=True)
+def _leave_graph_mode():
+    yield
+    from mmdfn_b200 import ops
+    ops.set_step_state(None)
+
+
+def test_graph_replays_match_eager_steps():
+    dev = torch.device("cuda", 0)
+    mm, model_e, batches = _build(dev, 0.0)
+    tr_e = _trainer(mm, model_e)
+    eager = []
+    for k in range(6):
+        t, a, v, q, u, lab = batches[k % 3]
+        eager.append(float(tr_e.step(t, q, u, LENGTHS, a, v, lab)))
+    p_eager = tr_e.flat_p.clone()
+
+    mm, model_g, batches = _build(dev, 0.0)
+    tr_g = _trainer(mm, model_g)
+    t, a, v, q, u, lab = batches[0]
+    graph = [float(tr_g.step(t, q, u, LENGTHS, a, v, lab))]                 # step 1 eager (also warms the library up)
+    tr_g.capture(t, q, u, LENGTHS, a, v, lab, warmup=0)
+    for k in range(1, 6):
+        t, a, v, q, u, lab = batches[k % 3]
+        graph.append(float(tr_g.replay(t, q, u, a, v, lab)))
+    assert tr_g.step_count == 6
+    assert int(tr_g._state[0]) == 6                                         # device-side step index
+    for le, lg in zip(eager, graph):
+        assert abs(le - lg) < 2e-5, (eager, graph)
+    # same Adam trajectory (split-K atomics make the two runs differ in the last bits only)
+    assert float((tr_g.flat_p - p_eager).abs().max()) < 5e-5
+
+
+def test_graph_replays_draw_fresh_dropout_masks():
+    dev = torch.device("cuda", 0)
+    mm, model, batches = _build(dev, 0.4)
+    tr = _trainer(mm, model, lr=0.0)                                        # frozen weights: only the masks change the loss
+    t, a, v, q, u, lab = batches[0]
+    tr.step(t, q, u, LENGTHS, a, v, lab)
+    tr.capture(t, q, u, LENGTHS, a, v, lab, warmup=0)
+    losses = [float(tr.replay(t, q, u, a, v, lab)) for _ in range(4)]
+    assert all(l == l for l in losses)
+    assert len({round(l, 6) for l in losses}) == 4, losses
