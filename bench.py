@@ -441,9 +441,22 @@ def main():
             r = cpu_reference_steps(steps=3, warmup=1, max_seconds=60.0)
             line["cpu_baseline"] = {"value": r["utt_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
         print(json.dumps(line), file=real_stdout, flush=True)
+    # Teardown.  A captured CUDA graph that contains NCCL kernels keeps the communicator busy: destroy_process_group()
+    # then waits for the graph to be destroyed and the process hangs after its result line (seen once at N=2: 10 min until
+    # the outer timeout).  So: drop the graph first, leave through os._exit once every rank is done, and keep a watchdog
+    # that ends the process if anything in the teardown still blocks.
+    watchdog = threading.Timer(45.0, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
+    torch.cuda.synchronize()
+    if getattr(trainer, "_graph", None) is not None:
+        trainer._graph.reset()
+        trainer._graph = None
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
