@@ -96,3 +96,15 @@ def test_dropin_module_names_import():
         sys.path.remove(d)
         for name in ("model", "model_GCN", "model_mm", "loss", "_bootstrap"):
             sys.modules.pop(name, None)
+
+
+def test_gru_tile_planner_fits_one_wave():
+    """ops.plan_gru_tiles: both concurrently running encoders must be co-resident (2 * ceil(n / nb) CTAs each, 148 SMs),
+    tiles come from the kernels' instantiations, and hopeless cases fall back to the library default (0, 0)."""
+    from mmdfn_b200 import ops
+    for T, n_a, n_b in ((100, 32, 192), (100, 31, 186), (24, 16, 432), (110, 32, 192), (30, 1, 6), (100, 8, 48)):
+        a, b = ops.plan_gru_tiles(T, n_a, n_b)
+        assert a in (2, 3, 4, 8) and b in (2, 3, 4, 8)
+        assert 2 * -(-n_a // a) + 2 * -(-n_b // b) <= 148
+    assert ops.plan_gru_tiles(100, 32, 192) == (4, 3)          # the bench shard: 16 + 128 CTAs
+    assert ops.plan_gru_tiles(500, 64, 1536) == (0, 0)         # BASELINE config 5: more sequences than one wave holds
