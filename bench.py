@@ -54,13 +54,32 @@ def workload_config(n_gpus):
             "l2_policy": f"inputs rotate over {N_BATCHES} distinct batches ({N_BATCHES * per_gpu_bytes / 1e6:.0f} MB > 126 MB L2)"}
 
 
+def synthetic_batch(lengths, seed):
+    """Seeded synthetic batch in the reference's collate layout (code/dataloader.py:31-34): time-major zero-padded
+    features, one-hot qmask (zero on padding), umask, packed labels.  (Own generator: the product arm of this file does
+    not import anything from oracle/.)"""
+    rs = np.random.RandomState(seed)
+    B, T = len(lengths), int(max(lengths))
+
+    def feat(d):
+        x = rs.standard_normal((T, B, d)).astype(np.float32)
+        for b, L in enumerate(lengths):
+            x[L:, b] = 0
+        return torch.from_numpy(x)
+
+    textf, acouf, visuf = feat(D_T), feat(D_A), feat(D_V)
+    spk = rs.randint(0, SPEAKERS, size=(T, B))
+    qmask = np.zeros((T, B, SPEAKERS), np.float32)
+    umask = np.zeros((B, T), np.float32)
+    for b, L in enumerate(lengths):
+        qmask[np.arange(L), b, spk[:L, b]] = 1
+        umask[b, :L] = 1
+    label = torch.from_numpy(np.concatenate([rs.randint(0, CLASSES, size=L) for L in lengths]).astype(np.int64))
+    return textf, acouf, visuf, torch.from_numpy(qmask), torch.from_numpy(umask), label
+
+
 def make_batches(n, seed0):
-    import mmdfn_oracle as O
-    out = []
-    for i in range(n):
-        t, a, v, q, u, lab = O.synthetic_batch([UTT] * DIALOGUES_PER_GPU, D_T, D_A, D_V, SPEAKERS, CLASSES, seed=seed0 + i)
-        out.append((t, a, v, q, u, lab))
-    return out
+    return [synthetic_batch([UTT] * DIALOGUES_PER_GPU, seed0 + i) for i in range(n)]
 
 
 def class_weights():
@@ -198,32 +217,64 @@ def roofline_graph_conv(dev, n_dialogues=DIALOGUES_PER_GPU):
     dg = [torch.rand(3, N, device=dev, generator=g) / UTT for _ in range(copies)]
     z = [torch.randn(3 * N, G, device=dev, generator=g) for _ in range(copies)]
     y = [torch.empty(3 * N, G, device=dev) for _ in range(copies)]
-    st = stream()
-
     def launch(i):
-        call("mmdfn_adj_spmm", *geom.args(), ptr(blk[i]), ptr(dg[i]), ptr(z[i]), G, ptr(y[i]), st)
+        call("mmdfn_adj_spmm", *geom.args(), ptr(blk[i]), ptr(dg[i]), ptr(z[i]), G, ptr(y[i]), stream())
 
-    for i in range(copies):
-        launch(i)
-    torch.cuda.synchronize()
+    half = alg_bytes // 8
+    src = [torch.empty(half, device=dev) for _ in range(copies)]
+    dst = [torch.empty(half, device=dev) for _ in range(copies)]
+
+    def launch_copy(i):
+        torch.mul(src[i], 1.0, out=dst[i])            # an SM kernel (a D2D copy_ would become a copy-engine memcpy node)
+
     reps = 3 * copies
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(reps):
-        launch(i % copies)
-    e1.record()
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / reps
+
+    def timed_us(fn):
+        """average duration of `reps` back-to-back launches over rotating operands, CUDA events on the launching stream.
+        The launches are replayed from a captured CUDA graph so that the host's launch rate (5-10 us per ctypes / torch
+        call, comparable to the kernel itself at this size) is not part of the measurement; eager loop as a fallback."""
+        for i in range(copies):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(reps):
+                    fn(i % copies)
+            g.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            mode = "graph replay"
+        except Exception:  # pragma: no cover
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(reps):
+                fn(i % copies)
+            e1.record()
+            torch.cuda.synchronize()
+            mode = "eager loop"
+        return e0.elapsed_time(e1) * 1e3 / reps, mode
+
+    us, mode = timed_us(launch)
+    # context for the fraction: a plain device-to-device copy kernel that moves the same number of bytes (half read, half
+    # written), timed with the same protocol -- what ONE launch of this size can reach at all
+    us_copy, _ = timed_us(launch_copy)
     peak, how = measured_peak_gbs()
     achieved = alg_bytes / (us * 1e-6) / 1e9
     return {"kernel": "adj_spmm_tc_kernel (k6 graph-conv message aggregate hi = A_hat z; tcgen05 3xTF32, fp32-level accuracy)", "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel inside a training step
-            # (ncu --set full, profiles/r01_ncu_adj_spmm_tc_s2.csv: 7.76 MB read, 0 written -- z is partly L2-resident
+            # (ncu --set full, profiles/r01_ncu_adj_spmm_tc_s2_final.csv: 7.76 MB read, 0 written -- z is partly L2-resident
             # and the 3.84 MB of output stay in L2 for the consumer)
-            "traffic": 7761152 if n_dialogues == DIALOGUES_PER_GPU else None,
+            "traffic": 7761920 if n_dialogues == DIALOGUES_PER_GPU else None,
             "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us, "peak_source": how,
-            "note": "launch covers one GCN layer of the %dx100 shard; operands rotated over %d copies (> L2)" % (n_dialogues, copies)}
+            "same_bytes_copy_kernel": {"us_per_launch": us_copy, "frac": alg_bytes / (us_copy * 1e-6) / 1e9 / peak},
+            "note": "launch covers one GCN layer of the %dx100 shard; %d back-to-back launches (%s), operands rotated over "
+                    "%d copies (> L2)" % (n_dialogues, reps, mode, copies)}
 
 
 def _claim_stdout():
@@ -266,19 +317,17 @@ def main():
     import mmdfn_b200
     from mmdfn_b200.dp import FlatAdamTrainer
     from mmdfn_b200._lib import query
-    import mmdfn_oracle as O
-    from helpers import model_shapes
 
     W = max(3, args.warmup)
     K = max(1, args.steps)
     import contextlib
+    torch.manual_seed(2021)                               # random-init weights of the architecture (the reference's seed_everything(2021))
     with contextlib.redirect_stdout(sys.stderr):          # the constructor prints "construct GDF" like the reference; stdout is for the JSON line only
         model = mmdfn_b200.DialogueGNNModel(
             "LSTM", D_T, 150, 150, 100, 100, 100, 100, n_speakers=SPEAKERS, max_seq_len=200, window_past=10, window_future=10,
             n_classes=CLASSES, dropout=DROPOUT, graph_type="GDF", alpha=0.2, lamda=0.5, D_m_v=D_V, D_m_a=D_A, modals="avl",
             att_type="concat_subsequently", Deep_GCN_nlayers=LAYERS, use_speaker=False, reason_flag=True, use_crn_speaker=True,
             speaker_weights=SPK_W)
-    model.load_state_dict(O.formula_weights(model_shapes(D_T, D_A, D_V, SPEAKERS, CLASSES, LAYERS)))   # random-init weights
     model = model.to(dev).train()
     loss_fn = mmdfn_b200.FocalLoss(gamma=GAMMA, alpha=class_weights().to(dev))
     trainer = FlatAdamTrainer(model, loss_fn, lr=LR, weight_decay=L2)
@@ -434,7 +483,7 @@ def main():
         try:
             line["roofline"] = roofline_graph_conv(dev)
             big = roofline_graph_conv(dev, 256)          # BASELINE config 4 on one GPU (256 x 100 utterances): steady-state view
-            line["roofline"]["at_256_dialogues"] = {k: big[k] for k in ("achieved", "frac", "us_per_launch", "algorithmic_bytes_per_launch")}
+            line["roofline"]["at_256_dialogues"] = {k: big[k] for k in ("achieved", "frac", "us_per_launch", "algorithmic_bytes_per_launch", "same_bytes_copy_kernel")}
         except Exception as e:  # pragma: no cover
             line["roofline"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:

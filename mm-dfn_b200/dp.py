@@ -128,7 +128,12 @@ class FlatAdamTrainer:
 
     def replay(self, textf, qmask, umask, acouf, visuf, label):
         """One captured step on a new batch of the captured shapes; returns the (static) loss tensor."""
+        if self._graph is None:
+            raise RuntimeError("replay() needs a captured step: call capture() first")
         for dst, src in zip(self._static, (textf, qmask, umask, acouf, visuf, label)):
+            if src.shape != dst.shape or src.dtype != dst.dtype:
+                raise ValueError(f"replay() got a tensor of shape {tuple(src.shape)} / {src.dtype}; the captured step takes "
+                                 f"{tuple(dst.shape)} / {dst.dtype} (capture one graph per batch geometry)")
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()

@@ -8,17 +8,15 @@ import torch
 import bench as B
 import mmdfn_b200
 from mmdfn_b200.dp import FlatAdamTrainer
-import mmdfn_oracle as O
-from helpers import model_shapes
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
+torch.manual_seed(2021)
 model = mmdfn_b200.DialogueGNNModel(
     "LSTM", B.D_T, 150, 150, 100, 100, 100, 100, n_speakers=B.SPEAKERS, max_seq_len=200, window_past=10, window_future=10,
     n_classes=B.CLASSES, dropout=B.DROPOUT, graph_type="GDF", alpha=0.2, lamda=0.5, D_m_v=B.D_V, D_m_a=B.D_A, modals="avl",
     att_type="concat_subsequently", Deep_GCN_nlayers=B.LAYERS, use_speaker=False, reason_flag=True, use_crn_speaker=True,
     speaker_weights=B.SPK_W)
-model.load_state_dict(O.formula_weights(model_shapes(B.D_T, B.D_A, B.D_V, B.SPEAKERS, B.CLASSES, B.LAYERS)))
 model = model.to(dev).train()
 loss_fn = mmdfn_b200.FocalLoss(gamma=B.GAMMA, alpha=B.class_weights().to(dev))
 trainer = FlatAdamTrainer(model, loss_fn, lr=B.LR, weight_decay=B.L2)
