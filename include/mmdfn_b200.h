@@ -208,6 +208,22 @@ int mmdfn_window_sum(int N, int G, int reach_back, int reach_fwd, const int* dia
 /* out[b][c][r] = in[b][r][c] */
 int mmdfn_transpose_batched(int batch, int rows, int cols, const float* in, float* out, void* stream);
 
+/* ---- a13: MMGatedAttention 'general' (code/model.py:757-781) -------------------------------------
+ * h_m = tanh(P_m), P_m = W_m x_m + b_m (computed by the caller with mmdfn_gemm); z_mn = sigmoid(w_mn.[x_m, x_n, x_m*x_n]
+ * + b_mn) for the pairs av, al, vl; out (N, 3C) = [z_av h_a + (1-z_av) h_v | z_al h_a + (1-z_al) h_l | z_vl h_v +
+ * (1-z_vl) h_l].  x* (N, D) are the (dropped-out) inputs, w (3, 3D) = transform_av/al/vl.weight stacked, b (3) their
+ * biases, z (N, 3) is saved for the backward.  Backward: dP* (N, C) and dx* (N, D) (the gate path only; the GEMMs'
+ * backward adds the projection path), dw (3, 3D), db (3) are overwritten; dzpre_ws is an (N, 3) scratch. */
+int mmdfn_gated_fuse_fwd(int N, int D, int C, const float* xa, const float* xv, const float* xl, const float* Pa,
+                         const float* Pv, const float* Pl, const float* w, const float* b, float* out, float* z,
+                         void* stream);
+int mmdfn_gated_fuse_bwd(int N, int D, int C, const float* dout, const float* xa, const float* xv, const float* xl,
+                         const float* Pa, const float* Pv, const float* Pl, const float* w, const float* b,
+                         const float* z, float* dPa, float* dPv, float* dPl, float* dxa, float* dxv, float* dxl,
+                         float* dw, float* db, float* dzpre_ws, void* stream);
+/* y = mask ? x * scale : 0 (nn.Dropout with an explicit keep mask, code/model.py:742-744; its own backward) */
+int mmdfn_mask_scale(long long n, const float* x, const unsigned char* mask, float scale, float* y, void* stream);
+
 /* ---- support: dropout keep masks, fused flat-buffer Adam(+L2) (code/run_train_erc.py:512) ----- */
 int mmdfn_dropout_mask(long long n, float p, unsigned long long seed, unsigned long long offset,
                        unsigned char* mask, void* stream);

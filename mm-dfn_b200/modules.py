@@ -288,8 +288,24 @@ class MMGatedAttention(nn.Module):
             self.transform_al = nn.Linear(mem_dim * 3, 1)
             self.transform_vl = nn.Linear(mem_dim * 3, 1)
 
-    def forward(self, a, v, l, modals=None):
-        raise NotImplementedError("att_type='gated' is an ablation outside the MM-DFN hot path (SURVEY 8f rank 4)")
+    def forward(self, a, v, l, modals=None, masks=None):
+        """(N, mem_dim) x 3 -> (N, 3 * cand_dim) for att_type='general' with all three modalities (code/model.py:741-781).
+        Dropout(0.5) on each input in train mode; `masks` (tests only) injects the three uint8 keep-masks (a, v, l)."""
+        if self.att_type != 'general' or modals is None or not all(m in modals for m in 'avl'):
+            raise NotImplementedError("MMGatedAttention: only att_type='general' with modals containing a, v and l")
+        xs = [a, v, l]
+        if masks is not None or self.training:
+            p = 0.5
+            if masks is None:
+                masks = ops.make_masks([tuple(x.shape) for x in xs], p, a.device)
+            xs = [ops.MaskScaleFn.apply(x, m, 1.0 / (1.0 - p)) for x, m in zip(xs, masks)]
+        Pa = ops.LinearFn.apply(xs[0], self.transform_a.weight, self.transform_a.bias)
+        Pv = ops.LinearFn.apply(xs[1], self.transform_v.weight, self.transform_v.bias)
+        Pl = ops.LinearFn.apply(xs[2], self.transform_l.weight, self.transform_l.bias)
+        # the three (1, 3D) gate weights / (1,) biases as one (3, 3D) / (3,) operand; torch.cat only moves data
+        w = torch.cat([self.transform_av.weight, self.transform_al.weight, self.transform_vl.weight], dim=0)
+        b = torch.cat([self.transform_av.bias, self.transform_al.bias, self.transform_vl.bias], dim=0)
+        return ops.GatedFuseFn.apply(xs[0], xs[1], xs[2], Pa, Pv, Pl, w, b)
 
 
 def simple_batch_graphify(features, lengths, no_cuda):

@@ -135,6 +135,57 @@ class LinearFn(torch.autograd.Function):
         return dx, dw, db
 
 
+class MaskScaleFn(torch.autograd.Function):
+    """y = mask ? x * scale : 0  (nn.Dropout with an explicit uint8 keep mask)."""
+
+    @staticmethod
+    def forward(ctx, x, mask, scale):
+        x = _f32c(x)
+        y = _empty(x.shape, x.device)
+        call("mmdfn_mask_scale", x.numel(), ptr(x), ptr(mask, U8), float(scale), ptr(y), stream())
+        ctx.mask, ctx.scale = mask, float(scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _f32c(dy)
+        dx = _empty(dy.shape, dy.device)
+        call("mmdfn_mask_scale", dy.numel(), ptr(dy), ptr(ctx.mask, U8), ctx.scale, ptr(dx), stream())
+        return dx, None, None
+
+
+class GatedFuseFn(torch.autograd.Function):
+    """MMGatedAttention 'general' after the three projections (code/model.py:761-781): gates from the inputs, tanh of
+    the projections, the three pairwise mixes.  w (3, 3D) / b (3): transform_av/al/vl stacked."""
+
+    @staticmethod
+    def forward(ctx, xa, xv, xl, Pa, Pv, Pl, w, b):
+        xa, xv, xl, Pa, Pv, Pl, w, b = (_f32c(t) for t in (xa, xv, xl, Pa, Pv, Pl, w, b))
+        N, D = xa.shape
+        C = Pa.shape[1]
+        out = _empty((N, 3 * C), xa.device)
+        z = _empty((N, 3), xa.device)
+        call("mmdfn_gated_fuse_fwd", N, D, C, ptr(xa), ptr(xv), ptr(xl), ptr(Pa), ptr(Pv), ptr(Pl), ptr(w), ptr(b),
+             ptr(out), ptr(z), stream())
+        ctx.save_for_backward(xa, xv, xl, Pa, Pv, Pl, w, b, z)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xa, xv, xl, Pa, Pv, Pl, w, b, z = ctx.saved_tensors
+        N, D = xa.shape
+        C = Pa.shape[1]
+        dout = _f32c(dout)
+        dev = xa.device
+        dP = [_empty((N, C), dev) for _ in range(3)]
+        dx = [_empty((N, D), dev) for _ in range(3)]
+        dw, db, ws = _empty((3, 3 * D), dev), _empty((3,), dev), _empty((N, 3), dev)
+        call("mmdfn_gated_fuse_bwd", N, D, C, ptr(dout), ptr(xa), ptr(xv), ptr(xl), ptr(Pa), ptr(Pv), ptr(Pl), ptr(w), ptr(b),
+             ptr(z), ptr(dP[0]), ptr(dP[1]), ptr(dP[2]), ptr(dx[0]), ptr(dx[1]), ptr(dx[2]), ptr(dw), ptr(db), ptr(ws),
+             stream())
+        return dx[0], dx[1], dx[2], dP[0], dP[1], dP[2], dw, db
+
+
 class Proj3Fn(torch.autograd.Function):
     """U (3,T,B,200) = stack over (a, v, l) of x_m W_m^T + b_m   (code/model.py:1065,1094,1129)."""
 
