@@ -221,6 +221,9 @@ int mmdfn_gated_fuse_bwd(int N, int D, int C, const float* dout, const float* xa
                          const float* Pa, const float* Pv, const float* Pl, const float* w, const float* b,
                          const float* z, float* dPa, float* dPv, float* dPl, float* dxa, float* dxv, float* dxl,
                          float* dw, float* db, float* dzpre_ws, void* stream);
+/* log_softmax over the class axis and its backward (the relation path's 'gated' head, code/model.py:1238-1239) */
+int mmdfn_log_softmax_fwd(int N, int C, const float* logits, float* log_prob, void* stream);
+int mmdfn_log_softmax_bwd(int N, int C, const float* log_prob, const float* dlog_prob, float* dlogits, void* stream);
 /* y = mask ? x * scale : 0 (nn.Dropout with an explicit keep mask, code/model.py:742-744; its own backward) */
 int mmdfn_mask_scale(long long n, const float* x, const unsigned char* mask, float scale, float* y, void* stream);
 

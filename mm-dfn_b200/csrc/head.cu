@@ -296,3 +296,24 @@ extern "C" int mmdfn_adam_step_dev(long long n, float* param, const float* grad,
   MMDFN_LAUNCH_CHECK();
   return 0;
 }
+
+// stand-alone log_softmax over the class axis (the relation path's 'gated' head: dropout -> smax_fc -> log_softmax,
+// code/model.py:1238-1239); dlogits = dlp - exp(lp) * sum_c dlp
+extern "C" int mmdfn_log_softmax_fwd(int N, int C, const float* logits, float* log_prob, void* stream) {
+  if (!logits || !log_prob) return MMDFN_ENULL;
+  if (C <= 0 || N < 0) return MMDFN_EINVAL;
+  if (N == 0) return 0;
+  log_softmax_kernel<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(N, C, logits, log_prob);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmdfn_log_softmax_bwd(int N, int C, const float* log_prob, const float* dlog_prob, float* dlogits,
+                                     void* stream) {
+  if (!log_prob || !dlog_prob || !dlogits) return MMDFN_ENULL;
+  if (C <= 0 || N < 0) return MMDFN_EINVAL;
+  if (N == 0) return 0;
+  log_softmax_bwd_kernel<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(N, C, log_prob, dlog_prob, dlogits);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}

@@ -327,11 +327,13 @@ class DialogueGNNModel(nn.Module):
                  reason_flag=False, multi_modal=True, use_crn_speaker=False, speaker_weights='1-1-1', modal_weight=1.0):
         super().__init__()
         if base_model != 'LSTM' or not multi_modal or sorted(modals) != ['a', 'l', 'v'] \
-                or graph_type not in ('GDF', 'relation') or att_type != 'concat_subsequently' or av_using_lstm \
+                or graph_type not in ('GDF', 'relation') or av_using_lstm \
+                or not (att_type == 'concat_subsequently' or (att_type == 'gated' and graph_type == 'relation')) \
                 or D_e != 100 or graph_hidden_size != 100 or not use_residue or (graph_type == 'relation' and use_GCN):
             raise NotImplementedError(
                 "mmdfn_b200 implements the MM-DFN hot path only: base_model='LSTM', multi_modal, modals='avl', "
-                "graph_type='GDF' (or 'relation'), att_type='concat_subsequently', D_e=graph_hidden_size=100, use_residue")
+                "graph_type='GDF' (or 'relation'), att_type='concat_subsequently' (or 'gated' with graph_type='relation'), "
+                "D_e=graph_hidden_size=100, use_residue")
         self.base_model, self.avec, self.no_cuda, self.graph_type = base_model, avec, no_cuda, graph_type
         self.alpha, self.lamda, self.multiheads, self.graph_construct = alpha, lamda, multiheads, graph_construct
         self.use_topic, self.dropout, self.use_GCN, self.use_residue = use_topic, dropout, use_GCN, use_residue
@@ -381,7 +383,8 @@ class DialogueGNNModel(nn.Module):
                 self.edge_type_mapping[str(j) + str(k) + '1'] = len(self.edge_type_mapping)
         self.gatedatt = MMGatedAttention(2 * D_e + graph_hidden_size, graph_hidden_size, att_type='general')
         self.dropout_ = nn.Dropout(self.dropout)
-        self.smax_fc = nn.Linear(300 * len(self.modals), n_classes)
+        # code/model.py:984-990: the gated fusion feeds 100 features per modality pair into the classifier
+        self.smax_fc = nn.Linear((100 if att_type == 'gated' else 300) * len(self.modals), n_classes)
 
     def _gru_weights(self, gru):
         return [getattr(gru, k) for k in ops.GRU_KEYS]
@@ -444,7 +447,7 @@ class DialogueGNNModel(nn.Module):
         X = ops.PartyPackFn.apply(Utab, E_l, Q, geom, sel, pos, S, tuple(self.speaker_weights))
         m_h = pooled[2] if train_drop else mk.get("head")
         if self.graph_type == 'relation':
-            return self._forward_relation(X, E_l, qmask, geom, seq_lengths, umask, m_h, scale)
+            return self._forward_relation(X, E_l, qmask, geom, seq_lengths, umask, m_h, scale, mk.get("gated"))
         gm = mk.get("gcn") if masks is not None else None
         if pool_gcn:
             gm = {"x": pooled[3], "h0": pooled[4], "layers": pooled[5] if len(gcn.convs) > 0 else None}
@@ -452,7 +455,7 @@ class DialogueGNNModel(nn.Module):
         log_prob = ops.HeadFn.apply(F_, geom.N, m_h, scale, self.smax_fc.weight, self.smax_fc.bias)
         return log_prob, None, None, None, None
 
-    def _forward_relation(self, X, E_l, qmask, geom, seq_lengths, umask, m_h, scale):
+    def _forward_relation(self, X, E_l, qmask, geom, seq_lengths, umask, m_h, scale, gated_masks=None):
         """graph_type='relation' (code/model.py:1182-1242): windowed speaker/temporal edges, edge weights from
         MaskedEdgeAttention over the padded text-branch features (the reference calls batch_graphify once per modality
         with the same att_model and keeps the last = 'l' result), one RGCNConv->GraphConv network per modality,
@@ -466,6 +469,19 @@ class DialogueGNNModel(nn.Module):
         edges.edge_index._mmdfn_edges = edges
         edge_norm = rel.EdgeAttnFn.apply(M_l, self.att_model.scalar.weight, edges)
         args = (edges.edge_index, edge_norm, edges.edge_type, seq_lengths, umask, self.nodal_attention, self.avec)
+        if self.att_type == 'gated':
+            # code/model.py:1235-1239: gatedatt over the three networks' features -> dropout -> smax_fc -> log_softmax.
+            # `gated_masks` (tests only): {'in': three uint8 keep-masks of the module's Dropout(0.5), 'head': (N, 300)}
+            gmk = gated_masks or {}
+            feat = self.gatedatt(self.graph_net_a(xa, *args), self.graph_net_v(xv, *args), self.graph_net_l(xl, *args),
+                                 self.modals, masks=gmk.get("in"))
+            m_g = gmk.get("head")
+            if m_g is None and self.training and float(self.dropout) > 0:
+                m_g = ops.make_mask((N, feat.shape[1]), float(self.dropout), feat.device)
+            if m_g is not None:
+                feat = ops.MaskScaleFn.apply(feat, m_g, 1.0 / (1.0 - float(self.dropout)))
+            log_prob = ops.LogSoftmaxFn.apply(ops.LinearFn.apply(feat, self.smax_fc.weight, self.smax_fc.bias))
+            return log_prob, edges.edge_index, edge_norm, edges.edge_type, list(edges.counts)
         F_ = torch.cat([self.graph_net_a(xa, *args), self.graph_net_v(xv, *args), self.graph_net_l(xl, *args)], dim=0)
         log_prob = ops.HeadFn.apply(F_, N, m_h, scale, self.smax_fc.weight, self.smax_fc.bias, False)
         return log_prob, edges.edge_index, edge_norm, edges.edge_type, list(edges.counts)

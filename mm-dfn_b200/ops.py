@@ -154,6 +154,28 @@ class MaskScaleFn(torch.autograd.Function):
         return dx, None, None
 
 
+class LogSoftmaxFn(torch.autograd.Function):
+    """log_softmax over dim 1 of (N, C) logits."""
+
+    @staticmethod
+    def forward(ctx, logits):
+        logits = _f32c(logits)
+        N, C = logits.shape
+        lp = _empty((N, C), logits.device)
+        call("mmdfn_log_softmax_fwd", N, C, ptr(logits), ptr(lp), stream())
+        ctx.save_for_backward(lp)
+        return lp
+
+    @staticmethod
+    def backward(ctx, dlp):
+        (lp,) = ctx.saved_tensors
+        N, C = lp.shape
+        dlp = _f32c(dlp)
+        dlogits = _empty((N, C), lp.device)
+        call("mmdfn_log_softmax_bwd", N, C, ptr(lp), ptr(dlp), ptr(dlogits), stream())
+        return dlogits
+
+
 class GatedFuseFn(torch.autograd.Function):
     """MMGatedAttention 'general' after the three projections (code/model.py:761-781): gates from the inputs, tanh of
     the projections, the three pairwise mixes.  w (3, 3D) / b (3): transform_av/al/vl stacked."""

@@ -63,8 +63,14 @@ def test_state_dict_matches_reference_manifest(tag, args):
 def test_unsupported_configurations_raise():
     with pytest.raises(NotImplementedError):
         mmdfn_b200.DialogueGNNModel("DialogRNN", 100, 150, 150, 100, 100, 100, 100, 2, 200, 10, 10, graph_type="GDF")
+    with pytest.raises(NotImplementedError):                      # the ctor's default att_type='gated' exists on 'relation' only
+        mmdfn_b200.DialogueGNNModel("LSTM", 100, 150, 150, 100, 100, 100, 100, 2, 200, 10, 10, graph_type="GDF")
     with pytest.raises(NotImplementedError):
-        mmdfn_b200.DialogueGNNModel("LSTM", 100, 150, 150, 100, 100, 100, 100, 2, 200, 10, 10, graph_type="relation")
+        mmdfn_b200.DialogueGNNModel("LSTM", 100, 150, 150, 100, 100, 100, 100, 2, 200, 10, 10, graph_type="relation",
+                                    att_type="mfn")
+    m = mmdfn_b200.DialogueGNNModel("LSTM", 100, 150, 150, 100, 100, 100, 100, 2, 200, 10, 10, graph_type="relation",
+                                    n_classes=6)              # defaults: att_type='gated' -> 300-wide classifier input
+    assert tuple(m.smax_fc.weight.shape) == (6, 300)          # code/model.py:986-988
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

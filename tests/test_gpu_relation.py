@@ -177,3 +177,50 @@ def test_dialogue_gnn_model_relation_graph_type(lengths, S):
             continue
         g, r = p.grad.cpu(), P[k].grad
         assert float((g - r).norm() / max(float(r.norm()), 1e-8)) < 1e-3, k
+
+
+def test_dialogue_gnn_model_relation_gated_attention():
+    """graph_type='relation', att_type='gated' (code/model.py:1235-1239): MMGatedAttention over the three networks'
+    features (its Dropout(0.5) masks injected) -> smax_fc (300 -> C) -> log_softmax; logits and all gradients vs the oracle."""
+    mm, ops, rel = _mods()
+    lengths, S, C, dT, dA, dV = [9, 14, 6], 2, 6, 100, 40, 24
+    N = sum(lengths)
+    t, a, v, q, u, lab = O.synthetic_batch(lengths, dT, dA, dV, S, C, seed=23)
+    m = mm.DialogueGNNModel("LSTM", dT, 150, 150, 100, 100, 100, 100, n_speakers=S, max_seq_len=200, window_past=10,
+                            window_future=10, n_classes=C, dropout=0.0, graph_type="relation", alpha=0.2, lamda=0.5,
+                            D_m_v=dV, D_m_a=dA, modals="avl", att_type="gated", Deep_GCN_nlayers=2,
+                            use_speaker=False, reason_flag=False, use_crn_speaker=True, speaker_weights="1-0.5-2")
+    assert tuple(m.smax_fc.weight.shape) == (C, 300)
+    m.load_state_dict(O.formula_weights({k: tuple(p.shape) for k, p in m.state_dict().items()}, seed=78))
+    P = {k: p.detach().clone().requires_grad_(True) for k, p in m.state_dict().items()}
+    rs = np.random.RandomState(5)
+    gmasks = [torch.from_numpy((rs.rand(N, 300) < 0.5).astype(np.uint8)) for _ in range(3)]
+    wts = (1.0, 0.5, 2.0)
+    U_a, U_v, U_l = (O.linear(x, P[f"linear_{n}.weight"], P[f"linear_{n}.bias"]) for x, n in ((a, "a"), (v, "v"), (t, "l")))
+    E_l = O.bigru2(U_l, P, "lstm_l")
+    em = [U_a + wts[0] * O.party_encode(U_a, q, P), U_v + wts[1] * O.party_encode(U_v, q, P), E_l + wts[2] * O.party_encode(U_l, q, P)]
+    ei, et, counts = O.build_edges(q.numpy(), lengths, 10, 10)
+    en = O.edge_norms(O.masked_edge_attention(em[2], P["att_model.scalar.weight"], lengths, 10, 10), lengths, 10, 10)
+    outs = []
+    for e, n in zip(em, "avl"):
+        x = O.ragged_pack(e, lengths)
+        h1 = O.rgcn_conv(x, ei, et, en, P[f"graph_net_{n}.conv1.basis"], P[f"graph_net_{n}.conv1.att"],
+                         P[f"graph_net_{n}.conv1.root"], P[f"graph_net_{n}.conv1.bias"])
+        h2 = O.pyg_graph_conv(h1, ei, P[f"graph_net_{n}.conv2.weight"], P[f"graph_net_{n}.conv2.lin.weight"],
+                              P[f"graph_net_{n}.conv2.lin.bias"])
+        outs.append(torch.cat([x, h2], -1))
+    feat = O.mm_gated_attention(*[o * mk.float() * 2.0 for o, mk in zip(outs, gmasks)], P)
+    lp_ref = torch.log_softmax(O.linear(feat, P["smax_fc.weight"], P["smax_fc.bias"]), 1)
+    loss_ref = O.focal_loss(lp_ref, lab, 1.0)
+    loss_ref.backward()
+    m = m.to(DEV).train()
+    lp = m(t.to(DEV), q.to(DEV), u.to(DEV), lengths, a.to(DEV), v.to(DEV),
+           masks={"gated": {"in": [mk.to(DEV) for mk in gmasks]}})[0]
+    assert float((lp.detach().cpu() - lp_ref.detach()).abs().max()) < 1e-4
+    mm.FocalLoss(gamma=1.0)(lp, lab.to(DEV)).backward()
+    for k, p in m.named_parameters():
+        if P[k].grad is None:
+            assert p.grad is None, k
+            continue
+        g, r = p.grad.cpu(), P[k].grad
+        assert float((g - r).norm() / max(float(r.norm()), 1e-8)) < 1e-3, k
