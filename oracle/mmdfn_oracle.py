@@ -509,6 +509,47 @@ def mm_gated_attention(a: Tensor, v: Tensor, l: Tensor, P: Dict[str, Tensor], pr
 
 
 # --------------------------------------------------------------------------------------
+# a13  MFN (att_type='mfn' ablation)                                  code/model_fusion.py:10-120
+# --------------------------------------------------------------------------------------
+def lstm_cell(x: Tensor, h: Tensor, c: Tensor, P: Dict[str, Tensor], prefix: str) -> Tuple[Tensor, Tensor]:
+    """nn.LSTMCell: gates i, f, g, o = split(W_ih x + b_ih + W_hh h + b_hh); c' = sig(f) c + sig(i) tanh(g); h' = sig(o) tanh(c')."""
+    g = linear(x, P[f"{prefix}.weight_ih"], P[f"{prefix}.bias_ih"]) + linear(h, P[f"{prefix}.weight_hh"], P[f"{prefix}.bias_hh"])
+    i, f, gg, o = g.chunk(4, dim=-1)
+    c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+    return torch.sigmoid(o) * torch.tanh(c2), c2
+
+
+def mfn_forward(x: Tensor, P: Dict[str, Tensor], prefix: str = "") -> Tensor:
+    """Dropout-free restatement of MFN.forward (code/model_fusion.py:62-120).  x (T, n, 900) = [l | a | v] (300 each)
+    -> (T, n, 400) = [h_l | h_a | h_v | mem].  Three LSTMCells run independently of the memory; per step the window
+    cStar = [c_{t-1} | c_t] (600) is re-weighted by a softmax attention (att1), squashed to the memory proposal cHat
+    (att2, tanh), and two sigmoid gates computed from [attended | mem_{t-1}] (gamma1, gamma2) update the 100-d memory:
+    mem_t = gamma1 * mem_{t-1} + gamma2 * cHat.  (out_fc1 / out_fc2 are constructed but never used.)"""
+    pre = (prefix + ".") if prefix else ""
+    lin = lambda name, z: linear(z, P[f"{pre}{name}.weight"], P[f"{pre}{name}.bias"])
+    T, n = x.shape[0], x.shape[1]
+    xs = {"l": x[:, :, :300], "a": x[:, :, 300:600], "v": x[:, :, 600:]}
+    h = {m: x.new_zeros(n, 100) for m in "lav"}
+    c = {m: x.new_zeros(n, 100) for m in "lav"}
+    mem = x.new_zeros(n, 100)
+    outs = []
+    for t in range(T):
+        prev_cs = torch.cat([c["l"], c["a"], c["v"]], dim=1)
+        for m in "lav":
+            h[m], c[m] = lstm_cell(xs[m][t], h[m], c[m], P, f"{pre}lstm_{m}")
+        c_star = torch.cat([prev_cs, c["l"], c["a"], c["v"]], dim=1)
+        attention = torch.softmax(lin("att1_fc2", torch.relu(lin("att1_fc1", c_star))), dim=1)
+        attended = attention * c_star
+        c_hat = torch.tanh(lin("att2_fc2", torch.relu(lin("att2_fc1", attended))))
+        both = torch.cat([attended, mem], dim=1)
+        gamma1 = torch.sigmoid(lin("gamma1_fc2", torch.relu(lin("gamma1_fc1", both))))
+        gamma2 = torch.sigmoid(lin("gamma2_fc2", torch.relu(lin("gamma2_fc1", both))))
+        mem = gamma1 * mem + gamma2 * c_hat
+        outs.append(torch.cat([h["l"], h["a"], h["v"], mem], dim=-1))
+    return torch.stack(outs)
+
+
+# --------------------------------------------------------------------------------------
 # deterministic, torch-version-independent weights and synthetic inputs (shared by the
 # golden generator, the tests and bench.py so that nothing has to travel to the GPU box)
 # --------------------------------------------------------------------------------------
