@@ -47,7 +47,7 @@ UNIT = "utterances/s"
 def workload_config(n_gpus):
     per_gpu_bytes = UTT * DIALOGUES_PER_GPU * (D_T + D_A + D_V + SPEAKERS) * 4
     return {"workload": "BASELINE configs[1]/[3] (SURVEY C4 shape): synthetic IEMOCAP-shape, 32 dialogues x 100 "
-                        "utterances per GPU, 100/512/1024-d T/A/V, S=2, C=6, 2 GCN layers + LSTM fusion gate, "
+                        "utterances per GPU, 100/512/1024-d T/A/V, S=2, C=6, %d GCN layers + LSTM fusion gate, " % LAYERS +
                         "crn-speaker encoders, dropout 0.4, FocalLoss(gamma=1), Adam(lr=1e-4, l2=1e-4)",
             "dialogues_per_gpu": DIALOGUES_PER_GPU, "utterances_per_dialogue": UTT, "global_dialogues": DIALOGUES_PER_GPU * n_gpus,
             "gcn_layers": LAYERS, "parallelism": f"dp{n_gpus} (dialogue shards, 1 NCCL all-reduce/step)",
@@ -297,7 +297,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured whole-step CUDA graph")
+    ap.add_argument("--layers", type=int, default=LAYERS, help="GCN layers (default 2 = BASELINE configs[1]; the authors' "
+                    "IEMOCAP script uses 16) -- any other value is an extra data point, not the headline workload")
     args = ap.parse_args()
+    globals()["LAYERS"] = max(0, args.layers)          # read by workload_config / the model constructor / the CPU port
     if args.impl == "reference":
         return run_reference_arm(args, real_stdout)
 

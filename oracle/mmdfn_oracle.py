@@ -511,7 +511,7 @@ def mm_gated_attention(a: Tensor, v: Tensor, l: Tensor, P: Dict[str, Tensor], pr
 # --------------------------------------------------------------------------------------
 # a13  MFN (att_type='mfn' ablation)                                  code/model_fusion.py:10-120
 # --------------------------------------------------------------------------------------
-def lstm_cell(x: Tensor, h: Tensor, c: Tensor, P: Dict[str, Tensor], prefix: str) -> Tuple[Tensor, Tensor]:
+def mfn_lstm_cell(x: Tensor, h: Tensor, c: Tensor, P: Dict[str, Tensor], prefix: str) -> Tuple[Tensor, Tensor]:
     """nn.LSTMCell: gates i, f, g, o = split(W_ih x + b_ih + W_hh h + b_hh); c' = sig(f) c + sig(i) tanh(g); h' = sig(o) tanh(c')."""
     g = linear(x, P[f"{prefix}.weight_ih"], P[f"{prefix}.bias_ih"]) + linear(h, P[f"{prefix}.weight_hh"], P[f"{prefix}.bias_hh"])
     i, f, gg, o = g.chunk(4, dim=-1)
@@ -536,7 +536,7 @@ def mfn_forward(x: Tensor, P: Dict[str, Tensor], prefix: str = "") -> Tensor:
     for t in range(T):
         prev_cs = torch.cat([c["l"], c["a"], c["v"]], dim=1)
         for m in "lav":
-            h[m], c[m] = lstm_cell(xs[m][t], h[m], c[m], P, f"{pre}lstm_{m}")
+            h[m], c[m] = mfn_lstm_cell(xs[m][t], h[m], c[m], P, f"{pre}lstm_{m}")
         c_star = torch.cat([prev_cs, c["l"], c["a"], c["v"]], dim=1)
         attention = torch.softmax(lin("att1_fc2", torch.relu(lin("att1_fc1", c_star))), dim=1)
         attended = attention * c_star
