@@ -1,3 +1,5 @@
+# What a round-end check runs on a 1-GPU B200 box (under /usr/local/graft/bin/gpurun -- 'bash tools/gpu_final.sh'):
+# GPU parity tests, the default bench line, smoke(), and the ncu launch list of an eager (--no-graph) bench run.
 set -x
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/tests.log
