@@ -12,7 +12,10 @@
  *   - every pointer is a DEVICE pointer to fp32 row-major contiguous data unless stated
  *     (int = int32, long long = int64, unsigned char = keep-mask bytes);
  *   - the caller (PyTorch) owns every input, output, saved-for-backward and workspace
- *     buffer; nothing is allocated or freed here and there is no hidden global state;
+ *     buffer; nothing is allocated or freed here.  The only process-global state is a handful of
+ *     host-side knobs read at enqueue time -- mmdfn_gru_set_tile, mmdfn_adj_spmm_set_variant,
+ *     mmdfn_gemm_tc_set_variant, the *_set_debug profiling hooks -- and the launch counter; they
+ *     are not thread-safe (the reference's trainer is single-threaded Python);
  *   - `stream` is a cudaStream_t; calls only enqueue work on it (asynchronous, re-entrant,
  *     CUDA-graph capturable);
  *   - return 0 on success, a positive cudaError_t value on a CUDA failure, a negative
