@@ -125,7 +125,8 @@ int mmdfn_adj_densify(int B, int N, int Lmax, const int* dia_off, const long lon
                       const float* adj_diag, float* dense, void* stream);
 
 /* timing aid: 0 (default) = the aggregate runs on tcgen05 when G == 100 and every dialogue has <= 128 utterances,
- * 1 = FFMA kernels only */
+ * 1 = FFMA kernels only, 2 = EXPERIMENTAL tcgen05 kernel for any dialogue length (128-row tiles, streamed contraction;
+ * opt-in until validated on hardware, see spmm_tc_long.cu) */
 int mmdfn_adj_spmm_set_variant(int variant);
 /* profiling aid: 64 x int64 device buffer receiving clock64() phase stamps of CTA 0 of the tcgen05 aggregate (NULL = off) */
 int mmdfn_adj_spmm_set_debug(long long* device_buf);

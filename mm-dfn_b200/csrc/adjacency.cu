@@ -289,13 +289,17 @@ __global__ void __launch_bounds__(256) adj_spmm100_kernel(AdjGeom g, const float
   }
 }
 
-static int g_spmm_variant = 0;   // 0 = tensor cores when eligible, 1 = FFMA kernels only (A/B timing, tools/)
+// 0 = tensor cores when eligible (L <= 128), 1 = FFMA kernels only (A/B timing, tools/), 2 = experimental tensor-core
+// kernel for any length (spmm_tc_long.cu; opt-in until validated on hardware)
+static int g_spmm_variant = 0;
 
 int adj_spmm(int B, int N, int Lmax, const int* dia_off, const i64* blk_off, const float* adj_blk,
              const float* adj_diag, const float* x, int G, float* y, cudaStream_t st) {
   if (B <= 0 || N <= 0 || Lmax <= 0) return 0;
   AdjGeom g{B, N, dia_off, blk_off};
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (G == SP_G && aligned && g_spmm_variant == 2)
+    return adj_spmm_tc_long(B, N, Lmax, dia_off, blk_off, adj_blk, adj_diag, x, y, st);
   if (G == SP_G && aligned && Lmax <= 128 && g_spmm_variant == 0)
     return adj_spmm_tc(B, N, dia_off, blk_off, adj_blk, adj_diag, x, y, st);
   if (G == SP_G && aligned) {
@@ -607,7 +611,7 @@ extern "C" int mmdfn_adj_bwd(int B, int N, int Lmax, const int* dia_off, const l
 }
 
 extern "C" int mmdfn_adj_spmm_set_variant(int variant) {
-  if (variant < 0 || variant > 1) return MMDFN_EINVAL;
+  if (variant < 0 || variant > 2) return MMDFN_EINVAL;
   mmdfn::g_spmm_variant = variant;
   return 0;
 }

@@ -21,6 +21,9 @@ int adj_spmm(int B, int N, int Lmax, const int* dia_off, const i64* blk_off, con
 // the same product on tcgen05 (3xTF32) for G == 100, every block <= 128 rows, 16-byte aligned x / y (spmm_tc.cu)
 int adj_spmm_tc(int B, int N, const int* dia_off, const i64* blk_off, const float* adj_blk, const float* adj_diag,
                 const float* x, float* y, cudaStream_t st);
+// experimental: the same on tcgen05 for any dialogue length (128-row tiles, streamed contraction; spmm_tc_long.cu)
+int adj_spmm_tc_long(int B, int N, int Lmax, const int* dia_off, const i64* blk_off, const float* adj_blk,
+                     const float* adj_diag, const float* x, float* y, cudaStream_t st);
 // P_blk (+)= sym(dhi z^T) ; P_diag (+)= sym cross terms
 int adj_grad_accum(int B, int N, int Lmax, const int* dia_off, const i64* blk_off, const float* dhi,
                    const float* z, int G, float* p_blk, float* p_diag, int accumulate, cudaStream_t st);

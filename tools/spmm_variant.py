@@ -1,4 +1,5 @@
-"""A/B of the two aggregate kernels (tcgen05 vs FFMA): max error against an fp64 dense product and time per launch."""
+"""A/B of the aggregate kernels (variant 0: tcgen05 for L <= 128 else FFMA, 1: FFMA only, 2: experimental any-length
+tcgen05 kernel): max error against an fp64 dense product and time per launch."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -58,7 +59,10 @@ def run(lengths, variant, reps=0):
 
 
 if __name__ == "__main__":
-    for lengths in ([100], [5, 3, 7], [128, 1, 37, 64, 99, 33], [100] * 32, [100] * 256, [96] * 32, [128] * 32, [64] * 32):
-        for v in (0, 1):
-            err, us = run(lengths, v, reps=200 if len(lengths) >= 32 else 0)
+    # variant 2 = the experimental any-length tcgen05 kernel (spmm_tc_long.cu): first the correctness-only cases, then timing
+    cases = ([100], [5, 3, 7], [128, 1, 37, 64, 99, 33], [129], [200, 17, 131], [500], [257, 3, 128, 255],
+             [100] * 32, [100] * 256, [96] * 32, [128] * 32, [64] * 32, [200] * 96, [500] * 24)
+    for lengths in cases:
+        for v in (0, 1, 2):
+            err, us = run(lengths, v, reps=200 if len(lengths) >= 24 else 0)
             print("lengths %s x%d variant %d: max err %.3g  %s" % (lengths[:6], len(lengths), v, err, "" if us is None else "%.2f us" % us), flush=True)
