@@ -87,70 +87,113 @@ def class_weights():
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle's faithful restatement of the reference algorithm (dense (3N)^2 adjacency,
-# per-dialogue loops, D.mm(adj).mm(D)), fwd + bwd (+Adam) on all host threads.
+# CPU baseline = the reference arm.  kind "reference": the UNMODIFIED reference (`code/model.py` DialogueGNNModel +
+# `code/loss.py` FocalLoss, staged byte for byte under baseline/_ref/code by __graft_entry__.build() and imported through
+# oracle/ref_shim.py), train mode with its own dropout, fwd + bwd + torch.optim.Adam on all host threads.  kind "port":
+# the oracle's faithful restatement of the same algorithm, only when the staged reference is absent.
 # ------------------------------------------------------------------------------------------------------
 def cpu_reference_steps(steps, warmup, n_dialogues=CPU_SAMPLE_DIALOGUES, max_seconds=150.0):
     import mmdfn_oracle as O
+    import ref_shim
     from helpers import model_shapes
     torch.set_num_threads(os.cpu_count() or 1)
     lengths = [UTT] * n_dialogues
     t, a, v, q, u, lab = O.synthetic_batch(lengths, D_T, D_A, D_V, SPEAKERS, CLASSES, seed=100)
-    P = {k: w.clone().requires_grad_(True) for k, w in O.formula_weights(model_shapes(D_T, D_A, D_V, SPEAKERS, CLASSES, LAYERS)).items()}
-    used = [w for k, w in P.items() if k.startswith(("linear_", "lstm_l.", "rnn_parties.", "graph_model.graph_net.", "smax_fc."))]
-    opt = torch.optim.Adam(used, lr=LR, weight_decay=L2)
     cw = class_weights()
-    wts = tuple(float(x) for x in SPK_W.split("-"))
-    gen = torch.Generator().manual_seed(0)
     T, B, N = UTT, n_dialogues, sum(lengths)
-    keep = 1.0 - DROPOUT
+    code_dir = ref_shim.ref_code_dir(ROOT)
+    if code_dir is not None:
+        kind = "reference"
+        model_mod, loss_mod, _, _ = ref_shim.reference_modules(code_dir)
+        torch.manual_seed(2021)
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):
+            model = ref_shim.make_reference_model(model_mod, D_T, D_A, D_V, SPEAKERS, CLASSES, LAYERS, "IEMOCAP", SPK_W, DROPOUT)
+        model.train()
+        loss_f = loss_mod.FocalLoss(gamma=GAMMA, alpha=cw)
+        opt = torch.optim.Adam(model.parameters(), lr=LR, weight_decay=L2)
 
-    def drop(shape):
-        return (torch.rand(shape, generator=gen) < keep).float() / keep
+        def one_step():
+            opt.zero_grad()
+            lp = model(t, q, u, lengths, a, v)[0]          # (textf, qmask, umask, lengths, acouf, visuf), code/run_train_erc.py:197
+            loss = loss_f(lp, lab)
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+    else:
+        kind = "port"
+        P = {k: w.clone().requires_grad_(True) for k, w in O.formula_weights(model_shapes(D_T, D_A, D_V, SPEAKERS, CLASSES, LAYERS)).items()}
+        used = [w for k, w in P.items() if k.startswith(("linear_", "lstm_l.", "rnn_parties.", "graph_model.graph_net.", "smax_fc."))]
+        opt = torch.optim.Adam(used, lr=LR, weight_decay=L2)
+        wts = tuple(float(x) for x in SPK_W.split("-"))
+        gen = torch.Generator().manual_seed(0)
+        keep = 1.0 - DROPOUT
 
-    def one_step():
-        masks = {"gru_l": drop((T, B, 200)),
-                 "gru_p": {m: [drop((T, B, 200)) for _ in range(SPEAKERS)] for m in "avl"},
-                 "gcn": {"x": drop((3 * N, 200)), "h0": drop((3 * N, 100)), "layer": [drop((3 * N, 100)) for _ in range(LAYERS)]},
-                 "head": drop((N, 900))}
-        opt.zero_grad(set_to_none=True)
-        lp = O.forward_gdf(P, t, q, lengths, a, v, nlayers=LAYERS, speaker_weights=wts, masks=masks, faithful=True)
-        loss = O.focal_loss(lp, lab, GAMMA, cw)
-        loss.backward()
-        opt.step()
-        return float(loss.detach())
+        def drop(shape):
+            return (torch.rand(shape, generator=gen) < keep).float() / keep
+
+        def one_step():
+            masks = {"gru_l": drop((T, B, 200)),
+                     "gru_p": {m: [drop((T, B, 200)) for _ in range(SPEAKERS)] for m in "avl"},
+                     "gcn": {"x": drop((3 * N, 200)), "h0": drop((3 * N, 100)), "layer": [drop((3 * N, 100)) for _ in range(LAYERS)]},
+                     "head": drop((N, 900))}
+            opt.zero_grad(set_to_none=True)
+            lp = O.forward_gdf(P, t, q, lengths, a, v, nlayers=LAYERS, speaker_weights=wts, masks=masks, faithful=True)
+            loss = O.focal_loss(lp, lab, GAMMA, cw)
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
 
     t_start = time.perf_counter()
+    warm_done = 0
     for _ in range(warmup):
         one_step()
+        warm_done += 1
         if time.perf_counter() - t_start > max_seconds / 3:
             break
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        one_step()
+        loss = one_step()
         times.append(time.perf_counter() - t0)
         if time.perf_counter() - t_start > max_seconds:
             break
+    assert np.isfinite(loss)
     sec = float(np.mean(times))
-    return {"utt_per_s": N / sec, "sec_per_step": sec, "steps_timed": len(times), "cores": torch.get_num_threads(),
+    return {"utt_per_s": N / sec, "sec_per_step": sec, "steps_timed": len(times), "warmup_done": warm_done,
+            "cores": torch.get_num_threads(), "kind": kind,
             "sample": f"{n_dialogues} of the workload's {DIALOGUES_PER_GPU} dialogues x {UTT} utterances per step "
                       f"({N} utterances; the reference's dense (3N)^2 adjacency makes its throughput fall with batch size), "
-                      f"fwd+bwd+Adam, dropout {DROPOUT}, mean of {len(times)} steps"}
+                      f"{'unmodified reference code/model.py' if kind == 'reference' else 'oracle port'}, "
+                      f"train mode, fwd+bwd+Adam, dropout {DROPOUT}, mean of {len(times)} steps after {warm_done} warm-up"}
+
+
+def reference_line(args, r):
+    return {"impl": "reference", "metric": METRIC, "value": r["utt_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": r["steps_timed"], "warmup": r["warmup_done"], "ms_per_step": r["sec_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus), "gpu_launches": 0,
+            "cpu_baseline": {"value": r["utt_per_s"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["utt_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
 def run_reference_arm(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_steps(max(1, args.steps), max(1, min(args.warmup, 2)), max_seconds=170.0)
-    line = {"impl": "reference", "metric": METRIC, "value": r["utt_per_s"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": r["steps_timed"], "warmup": min(args.warmup, 2), "ms_per_step": r["sec_per_step"] * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus), "gpu_launches": 0,
-            "cpu_baseline": {"value": r["utt_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
-            "e2e": {"value": r["utt_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), file=out, flush=True)
+    r = cpu_reference_steps(max(1, args.steps), max(1, args.warmup), n_dialogues=args.ref_dialogues, max_seconds=args.ref_seconds)
+    print(json.dumps(reference_line(args, r)), file=out, flush=True)
+
+
+def cpu_baseline_subprocess(layers):
+    """cpu_baseline of the product line: the reference arm run as its own process (the shim patches torch.Tensor
+    globally, which must not leak into the process that drives the GPU), bounded to ~60 s."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", "1", "--steps", "8", "--warmup", "2",
+                        "--layers", str(layers), "--ref-seconds", "60"], capture_output=True, text=True, timeout=400, env=env)
+    line = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")][-1]
+    return json.loads(line)["cpu_baseline"]
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -297,6 +340,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured whole-step CUDA graph")
+    ap.add_argument("--ref-dialogues", type=int, default=CPU_SAMPLE_DIALOGUES, help="reference arm: dialogues per CPU step")
+    ap.add_argument("--ref-seconds", type=float, default=170.0, help="reference arm: wall-clock bound of the whole run")
     ap.add_argument("--layers", type=int, default=LAYERS, help="GCN layers (default 2 = BASELINE configs[1]; the authors' "
                     "IEMOCAP script uses 16) -- any other value is an extra data point, not the headline workload")
     args = ap.parse_args()
@@ -490,8 +535,10 @@ def main():
         except Exception as e:  # pragma: no cover
             line["roofline"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_steps(steps=3, warmup=1, max_seconds=60.0)
-            line["cpu_baseline"] = {"value": r["utt_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+            try:
+                line["cpu_baseline"] = cpu_baseline_subprocess(LAYERS)
+            except Exception as e:  # pragma: no cover
+                line["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(line), file=real_stdout, flush=True)
     # Teardown.  A captured CUDA graph that contains NCCL kernels keeps the communicator busy: destroy_process_group()
     # then waits for the graph to be destroyed and the process hangs after its result line (seen once at N=2: 10 min until
@@ -501,9 +548,7 @@ def main():
     watchdog.daemon = True
     watchdog.start()
     torch.cuda.synchronize()
-    if getattr(trainer, "_graph", None) is not None:
-        trainer._graph.reset()
-        trainer._graph = None
+    trainer.release_graphs()
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()

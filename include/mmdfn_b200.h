@@ -124,9 +124,9 @@ int mmdfn_adj_bwd(int B, int N, int Lmax, const int* dia_off, const long long* b
 int mmdfn_adj_densify(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* adj_blk,
                       const float* adj_diag, float* dense, void* stream);
 
-/* timing aid: 0 (default) = the aggregate runs on tcgen05 when G == 100 and every dialogue has <= 128 utterances,
- * 1 = FFMA kernels only, 2 = EXPERIMENTAL tcgen05 kernel for any dialogue length (128-row tiles, streamed contraction;
- * opt-in until validated on hardware, see spmm_tc_long.cu) */
+/* timing / cross-check aid: 0 (default) = for G == 100 the aggregate runs on the any-length tcgen05 kernel (128-row
+ * tiles, streamed contraction; spmm_tc_long.cu), 1 = FFMA kernels only, 2 = the whole-block tcgen05 kernel
+ * (spmm_tc.cu) when every dialogue has <= 128 utterances */
 int mmdfn_adj_spmm_set_variant(int variant);
 /* profiling aid: 64 x int64 device buffer receiving clock64() phase stamps of CTA 0 of the tcgen05 aggregate (NULL = off) */
 int mmdfn_adj_spmm_set_debug(long long* device_buf);

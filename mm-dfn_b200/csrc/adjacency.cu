@@ -289,8 +289,10 @@ __global__ void __launch_bounds__(256) adj_spmm100_kernel(AdjGeom g, const float
   }
 }
 
-// 0 = tensor cores when eligible (L <= 128), 1 = FFMA kernels only (A/B timing, tools/), 2 = experimental tensor-core
-// kernel for any length (spmm_tc_long.cu; opt-in until validated on hardware)
+// 0 = automatic: the any-length tcgen05 kernel (spmm_tc_long.cu; validated on B200 in round 2 against fp64 products for
+// L = 1..500, profiles/r02_spmm_variant_long_kernel.log: as fast as the whole-block kernel at L <= 128, 2.6-3.7x the FFMA
+// fallback at L = 200..500); 1 = FFMA kernels only; 2 = the whole-block tcgen05 kernel (spmm_tc.cu) when every dialogue
+// has <= 128 utterances.  1 and 2 exist for A/B timing (tools/spmm_variant.py) and the cross-kernel parity tests.
 static int g_spmm_variant = 0;
 
 int adj_spmm(int B, int N, int Lmax, const int* dia_off, const i64* blk_off, const float* adj_blk,
@@ -298,10 +300,10 @@ int adj_spmm(int B, int N, int Lmax, const int* dia_off, const i64* blk_off, con
   if (B <= 0 || N <= 0 || Lmax <= 0) return 0;
   AdjGeom g{B, N, dia_off, blk_off};
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
-  if (G == SP_G && aligned && g_spmm_variant == 2)
-    return adj_spmm_tc_long(B, N, Lmax, dia_off, blk_off, adj_blk, adj_diag, x, y, st);
-  if (G == SP_G && aligned && Lmax <= 128 && g_spmm_variant == 0)
+  if (G == SP_G && aligned && Lmax <= 128 && g_spmm_variant == 2)
     return adj_spmm_tc(B, N, dia_off, blk_off, adj_blk, adj_diag, x, y, st);
+  if (G == SP_G && aligned && g_spmm_variant != 1)
+    return adj_spmm_tc_long(B, N, Lmax, dia_off, blk_off, adj_blk, adj_diag, x, y, st);
   if (G == SP_G && aligned) {
     static bool configured = false;
     if (!configured) {

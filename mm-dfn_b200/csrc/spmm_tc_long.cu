@@ -1,5 +1,5 @@
-// EXPERIMENTAL (opt-in through mmdfn_adj_spmm_set_variant(2); NOT yet validated on hardware -- written at the end of
-// round 1 after the GPU budget was spent; tools/spmm_variant.py checks it against an fp64 product and times it).
+// The default aggregate kernel for G = 100 (any dialogue length).  Validated on B200 in round 2
+// (profiles/r02_spmm_variant_long_kernel.log, tests/test_gpu_parity.py::test_aggregate_kernels_*).
 //
 // k6 on the tensor cores for dialogues of ANY length: the generalisation of spmm_tc.cu (same 3xTF32 tcgen05 scheme, same
 // operand layouts, same epilogue) from "one CTA = one whole (dialogue, modality) block of <= 128 utterances" to

@@ -15,13 +15,33 @@ import torch.distributed as dist
 
 from ._lib import call, ptr, stream
 
-# parameters that receive a gradient on the GDF path ("Used on GDF path")
-USED_PREFIXES = ("linear_a.", "linear_v.", "linear_l.", "lstm_l.", "rnn_parties.", "graph_model.graph_net.fcs.0.",
-                 "graph_model.graph_net.convs.", "graph_model.graph_net.rnn.", "smax_fc.")
+def used_prefixes(model):
+    """Name prefixes of the parameters that receive a gradient for THIS model configuration -- the set the reference's
+    Adam actually updates (parameters whose grad stays None are skipped by torch.optim.Adam, weight decay included;
+    SURVEY 8b "Used on GDF path").  Depends on graph_type / att_type / use_crn_speaker / reason_flag / layer count."""
+    pre = ["linear_a.", "linear_v.", "linear_l.", "lstm_l.", "smax_fc."]
+    if getattr(model, "use_crn_speaker", False):
+        pre.append("rnn_parties.")
+    if getattr(model, "graph_type", "GDF") == "relation":
+        pre += ["graph_net_a.", "graph_net_v.", "graph_net_l.", "att_model.scalar."]
+        if getattr(model, "att_type", "") == "gated":
+            pre.append("gatedatt.")
+    else:
+        net = model.graph_model.graph_net
+        pre += ["graph_model.graph_net.fcs.0.", "graph_model.graph_net.convs."]
+        if net.reason_flag and len(net.convs) > 0:
+            pre.append("graph_model.graph_net.rnn.")
+    return tuple(pre)
+
+
+# the scripted configuration (GDF, crn-speaker encoders, --reason_flag, K > 0): what tests/test_dp_gloo.py shards
+USED_PREFIXES = ("linear_a.", "linear_v.", "linear_l.", "lstm_l.", "smax_fc.", "rnn_parties.",
+                 "graph_model.graph_net.fcs.0.", "graph_model.graph_net.convs.", "graph_model.graph_net.rnn.")
 
 
 def used_parameters(model):
-    return [(n, p) for n, p in model.named_parameters() if n.startswith(USED_PREFIXES)]
+    pre = used_prefixes(model)
+    return [(n, p) for n, p in model.named_parameters() if n.startswith(pre)]
 
 
 def shard_dialogues(n_dialogues, rank, world):
@@ -60,7 +80,11 @@ class FlatAdamTrainer:
         self.total = total
         self.step_count = 0
         self._state = None            # device-resident step state (graph mode, see capture())
-        self._graph = None
+        self._graph = None            # most recently captured step
+        self._graphs = {}             # lengths tuple -> (graph, static inputs, static loss, n_global)
+        in_bucket = {id(p) for p in params}
+        self._outside = [(n, p) for n, p in model.named_parameters() if p.requires_grad and id(p) not in in_bucket]
+        self._checked = False
         if self.world > 1:                                        # replicas start identical
             dist.broadcast(self.flat_p, src=0, group=self.pg)
 
@@ -75,6 +99,15 @@ class FlatAdamTrainer:
         if n_global is not None and n_global != n_local:
             loss = loss * (float(n_local) / float(n_global))
         loss.backward()
+        if not self._checked:
+            # once per trainer: the bucket must hold exactly the parameters that receive a gradient -- a parameter
+            # outside it would silently stay at its initial value, one inside it without a gradient would be decayed
+            self._checked = True
+            stray = [n for n, p in self._outside if p.grad is not None]
+            missing = [n for n, p in zip(self.names, self.params) if p.grad is None]
+            if stray or missing:
+                raise RuntimeError(f"FlatAdamTrainer bucket mismatch: gradients outside the bucket {stray}, "
+                                   f"bucket parameters without a gradient {missing}")
         torch._foreach_copy_(self.grad_views, [p.grad for p in self.params])   # one multi-tensor gather into the bucket
         if self.world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
@@ -107,8 +140,9 @@ class FlatAdamTrainer:
         for dst, src in zip(self._static, (textf, qmask, umask, acouf, visuf, label)):
             dst.copy_(src)
         self._lengths, self._n_global = [int(x) for x in lengths], n_global
-        self._state = torch.zeros(2, dtype=torch.int64, device=dev)
-        self._state[0] = self.step_count
+        if self._state is None:                 # one device-resident step state shared by every captured geometry
+            self._state = torch.zeros(2, dtype=torch.int64, device=dev)
+            self._state[0] = self.step_count
         ops.set_step_state(self._state)
         t, q, u, a, v, lab = self._static
         side = torch.cuda.Stream(device=dev)
@@ -124,12 +158,32 @@ class FlatAdamTrainer:
         with torch.cuda.graph(self._graph):
             self._static_loss = self.step(t, q, u, self._lengths, a, v, lab, n_global)
         torch.cuda.synchronize(dev)
+        self._graphs[tuple(self._lengths)] = (self._graph, self._static, self._static_loss, n_global)
         return self
 
-    def replay(self, textf, qmask, umask, acouf, visuf, label):
-        """One captured step on a new batch of the captured shapes; returns the (static) loss tensor."""
+    def release_graphs(self):
+        """drop every captured step (needed before tearing down an NCCL communicator the graphs reference)"""
+        for g, _, _, _ in self._graphs.values():
+            g.reset()
+        self._graphs.clear()
+        self._graph = None
+
+    def has_graph(self, lengths):
+        return tuple(int(x) for x in lengths) in self._graphs
+
+    def replay(self, textf, qmask, umask, acouf, visuf, label, lengths=None):
+        """One captured step on a new batch of a captured geometry; returns the (static) loss tensor.  The captured
+        graph bakes in the dialogue lengths (row offsets, adjacency block offsets, label count, loss scale), not just the
+        padded shapes: pass `lengths` to select the graph captured for exactly these lengths (one graph per batch
+        geometry); without it the most recent capture is used and the caller vouches for identical lengths."""
         if self._graph is None:
             raise RuntimeError("replay() needs a captured step: call capture() first")
+        if lengths is not None:
+            key = tuple(int(x) for x in lengths)
+            if key not in self._graphs:
+                raise ValueError("replay(): no step was captured for these dialogue lengths (capture one graph per batch geometry)")
+            self._graph, self._static, self._static_loss, self._n_global = self._graphs[key]
+            self._lengths = list(key)
         for dst, src in zip(self._static, (textf, qmask, umask, acouf, visuf, label)):
             if src.shape != dst.shape or src.dtype != dst.dtype:
                 raise ValueError(f"replay() got a tensor of shape {tuple(src.shape)} / {src.dtype}; the captured step takes "

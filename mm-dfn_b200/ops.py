@@ -548,6 +548,9 @@ class GCNStackFn(torch.autograd.Function):
              tab, ptr(w_ih), ptr(w_hh), ptr(mask_x, U8), ptr(mask_h0, U8), ptr(mask_layers, U8), mask_scale,
              ptr(F_), ptr(ws), ptr(dF), ptr(dX), ptr(d_blk), ptr(d_diag), ptr(dW0), ptr(db0), dtab, ptr(dw_ih),
              ptr(dw_hh), ptr(db_ih), ptr(db_hh), 1, ptr(wsb), stream())
+        if not reason_flag or K == 0:
+            # the reference never touches the LSTM on this configuration: its grads stay None and Adam skips the weights
+            dw_ih = dw_hh = db_ih = db_hh = None
         return (dX, d_blk, d_diag, None, None, None, None, None, None, None, None, None,
                 dW0, db0, dw_ih, dw_hh, db_ih, db_hh, *dconv)
 

@@ -300,7 +300,12 @@ class RGCNConv(torch.nn.Module):
             p.data.uniform_(-bound, bound)
 
     def forward(self, x, edge_index, edge_type, edge_norm=None, size=None):
+        """`edge_type` must be the tensor batch_graphify produced for `edge_index`: the kernels recompute each edge's
+        type from the node speakers (2 (S spk_j + spk_i) + [j >= i], code/model.py:599-606) instead of reading it."""
         edges = _edges_of(edge_index)
+        if edge_type is not None and edge_type is not edges.edge_type and (
+                edge_type.shape != edges.edge_type.shape or not torch.equal(edge_type, edges.edge_type)):
+            raise NotImplementedError("RGCNConv: edge_type differs from the speaker/temporal relation types of this edge set")
         if edge_norm is None:
             edge_norm = torch.ones((edges.E,), device=x.device)
         return RGCNConvFn.apply(x, edge_norm, self.basis, self.att, self.root, self.bias, edges)
@@ -318,6 +323,10 @@ class GraphConv(torch.nn.Module):
         self.lin = torch.nn.Linear(in_channels, out_channels, bias=bias)
         bound = 1.0 / in_channels ** 0.5
         self.weight.data.uniform_(-bound, bound)
+        # PyG 1.4.3 GraphConv.reset_parameters(): uniform(in_channels, weight), then lin.reset_parameters() -- a SECOND
+        # draw for lin (nn.Linear already drew once in its constructor); mirrored so that later modules see the same
+        # RNG stream.  (Recalled from the published PyG source; PyG is not vendored: init parity on this path is unpinned.)
+        self.lin.reset_parameters()
 
     def forward(self, x, edge_index, edge_weight=None, size=None):
         if edge_weight is not None:

@@ -43,10 +43,59 @@ def model_shapes(d_text, d_audio, d_visual, S, C, K):
     return out
 
 
+def staged_pickle(rel):
+    """path of a reference feature pickle staged under baseline/_ref/data (git-ignored; __graft_entry__.build() copies
+    it from /root/reference; it travels to the GPU box with the snapshot) or None"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for base in (os.path.join(root, "baseline", "_ref", "data"), "/root/reference/data"):
+        p = os.path.join(base, rel)
+        if os.path.exists(p):
+            return p
+    return None
+
+
+_PKL = {}
+
+
+def iemocap_batch(vids):
+    """the reference's collate of these IEMOCAP dialogues (code/dataloader.py:18-34): time-major zero-padded features,
+    one-hot qmask ('M' -> [1,0]), umask"""
+    import pickle
+    path = staged_pickle("iemocap/IEMOCAP_features.pkl")
+    if path is None:
+        return None
+    if path not in _PKL:
+        _PKL[path] = pickle.load(open(path, "rb"), encoding="latin1")
+    ids, spk, labels, text, audio, visual = _PKL[path][:6]
+    lengths = [len(labels[v]) for v in vids]
+    T, B = max(lengths), len(vids)
+
+    def pad(src):
+        d = np.asarray(src[vids[0]]).shape[1]
+        out = np.zeros((T, B, d), np.float32)
+        for b, v in enumerate(vids):
+            out[:lengths[b], b] = np.asarray(src[v], dtype=np.float32)
+        return torch.from_numpy(out)
+
+    q = np.zeros((T, B, 2), np.float32)
+    u = np.zeros((B, T), np.float32)
+    for b, v in enumerate(vids):
+        for t_, x in enumerate(spk[v]):
+            q[t_, b, 0 if x == "M" else 1] = 1
+        u[b, :lengths[b]] = 1
+    return pad(text), pad(audio), pad(visual), torch.from_numpy(q), torch.from_numpy(u)
+
+
 def case_inputs(c, name):
     """(textf, acouf, visuf, qmask, umask, label, lengths) tensors of a golden case."""
     lengths = [int(x) for x in c["lengths"]]
-    if "textf" in c:
+    if "vids" in c:                      # real-size case: inputs come from the staged pickle (see make_golden_real.py)
+        got = iemocap_batch([str(x) for x in c["vids"]])
+        if got is None:
+            import pytest
+            pytest.skip("reference feature pickle not staged under baseline/_ref/data (run __graft_entry__.build() where /root/reference exists)")
+        t, a, v, q, u = got
+    elif "textf" in c:
         t, a, v, q, u = (torch.from_numpy(c[k]) for k in ("textf", "acouf", "visuf", "qmask", "umask"))
     else:
         seed = {"c4_synth_small": 4, "c5_synth_small": 5}[name]

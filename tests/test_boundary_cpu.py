@@ -114,3 +114,23 @@ def test_gru_tile_planner_fits_one_wave():
         assert 2 * -(-n_a // a) + 2 * -(-n_b // b) <= 148
     assert ops.plan_gru_tiles(100, 32, 192) == (4, 3)          # the bench shard: 16 + 128 CTAs
     assert ops.plan_gru_tiles(500, 64, 1536) == (0, 0)         # BASELINE config 5: more sequences than one wave holds
+
+
+def test_trainer_parameter_selection_follows_the_configuration():
+    """FlatAdamTrainer buckets the parameters the reference's Adam would update for each configuration."""
+    from types import SimpleNamespace as NS
+    from mmdfn_b200.dp import used_prefixes, USED_PREFIXES
+    net = NS(reason_flag=True, convs=[0, 1])
+    gdf = NS(graph_type="GDF", att_type="concat_subsequently", use_crn_speaker=True, graph_model=NS(graph_net=net))
+    assert sorted(used_prefixes(gdf)) == sorted(USED_PREFIXES)
+    gdf.use_crn_speaker = False
+    assert "rnn_parties." not in used_prefixes(gdf)
+    net.reason_flag = False
+    assert "graph_model.graph_net.rnn." not in used_prefixes(gdf)
+    net.reason_flag, net.convs = True, []
+    assert "graph_model.graph_net.rnn." not in used_prefixes(gdf)
+    rel = NS(graph_type="relation", att_type="gated", use_crn_speaker=True)
+    pre = used_prefixes(rel)
+    assert all(x in pre for x in ("graph_net_a.", "graph_net_v.", "graph_net_l.", "att_model.scalar.", "gatedatt."))
+    rel.att_type = "concat_subsequently"
+    assert "gatedatt." not in used_prefixes(rel)

@@ -79,3 +79,40 @@ def test_training_steps_reduce_loss():
     losses = [float(tr.step(*args)) for _ in range(12)]
     assert all(l == l for l in losses)                       # finite
     assert losses[-1] < 0.8 * losses[0], losses
+
+
+@pytest.mark.parametrize("cfg", [dict(graph_type="relation", att_type="concat_subsequently"),
+                                 dict(graph_type="relation", att_type="gated"),
+                                 dict(graph_type="GDF", use_crn_speaker=False),
+                                 dict(graph_type="GDF", reason_flag=False),
+                                 dict(graph_type="GDF", Deep_GCN_nlayers=0)])
+def test_trainer_buckets_exactly_the_parameters_that_get_gradients(cfg):
+    """every supported configuration: the flat bucket holds exactly the parameters that receive a gradient (the set
+    the reference's Adam updates) -- the trainer raises otherwise -- and training steps move all of them."""
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import mmdfn_b200
+    import mmdfn_oracle as O
+    from mmdfn_b200.dp import FlatAdamTrainer
+    dev = torch.device("cuda", 0)
+    kw = dict(n_speakers=2, max_seq_len=200, window_past=10, window_future=10, n_classes=6, dropout=0.0, graph_type="GDF",
+              alpha=0.2, lamda=0.5, D_m_v=48, D_m_a=64, modals="avl", att_type="concat_subsequently", Deep_GCN_nlayers=2,
+              use_speaker=False, reason_flag=True, use_crn_speaker=True, speaker_weights="3-0-1")
+    kw.update(cfg)
+    torch.manual_seed(5)
+    m = mmdfn_b200.DialogueGNNModel("LSTM", 100, 150, 150, 100, 100, 100, 100, **kw).to(dev).train()
+    t, a, v, q, u, lab = O.synthetic_batch(LENGTHS, 100, 64, 48, 2, 6, seed=2)
+    tr = FlatAdamTrainer(m, mmdfn_b200.FocalLoss(gamma=1.0), lr=2e-3, weight_decay=1e-5)
+    before = tr.flat_p.clone()
+    outside_before = {n: p.detach().clone() for n, p in tr._outside}
+    args = (t.to(dev), q.to(dev), u.to(dev), LENGTHS, a.to(dev), v.to(dev), lab.to(dev))
+    losses = [float(tr.step(*args)) for _ in range(6)]
+    assert losses[-1] < losses[0]
+    off = 0
+    for n, p in zip(tr.names, tr.params):
+        k = p.numel()
+        assert not torch.equal(before[off:off + k], tr.flat_p[off:off + k]), n        # every bucketed parameter moved
+        off += k
+    for n, p in tr._outside:
+        assert p.grad is None and torch.equal(p.detach(), outside_before[n]), n          # untouched, like the reference
