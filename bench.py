@@ -11,9 +11,10 @@ flat gradient bucket per step.
 
 One JSON line on rank 0.  `value` = whole-job utterances/s with inputs resident in HBM; `e2e` = the
 same step through the public API with pinned-host inputs copied H2D and the loss read back D2H every
-step; `roofline` = the graph-conv message-aggregate kernel (k6) timed alone with CUDA events against
-the measured HBM peak; `cpu_baseline` = the oracle's faithful port of the reference algorithm timed on
-the host cores on a bounded sample.  `--impl reference` times that CPU port only."""
+step; `roofline` = the fused graph-conv layer kernel (k6: aggregate + weight product + epilogue, one launch
+per layer) timed alone with CUDA events against the measured HBM peak; `cpu_baseline` = the UNMODIFIED
+reference (staged under baseline/_ref, imported through oracle/ref_shim.py) timed on the host cores on
+a bounded sample.  `--impl reference` times that CPU arm only."""
 import argparse
 import json
 import os
@@ -40,6 +41,9 @@ LR, L2 = 1e-4, 1e-4
 GAMMA = 1.0
 N_BATCHES = 8                      # distinct input batches rotated so that step inputs exceed L2
 CPU_SAMPLE_DIALOGUES = 8
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE gcn_layer_kernel<fwd> launch inside a training step of the default
+# workload, read from the committed `ncu --set full` capture (profiles/, see profiles/README.md); None = not captured yet
+NCU_TRAFFIC_BYTES = None
 METRIC = "utterances/sec (fwd+bwd) IEMOCAP-shape"
 UNIT = "utterances/s"
 
@@ -246,22 +250,38 @@ def measured_peak_gbs():
 
 
 def roofline_graph_conv(dev, n_dialogues=DIALOGUES_PER_GPU):
-    """k6 message aggregate hi = A_hat z on the bench shard, timed alone with CUDA events on the launching
-    stream; operands rotate over enough copies to defeat the 126 MB L2."""
+    """The fused graph-conv layer kernel (gcn_layer_kernel: message aggregate -> weight product -> theta/alpha mixes ->
+    ReLU -> dropout -> +q, ONE launch per layer) on the bench shard, timed alone with CUDA events on the launching
+    stream; operands rotate over enough copies to defeat the 126 MB L2.  Algorithmic bytes = SURVEY 8(d)'s per-layer
+    figure 4 [3NG (z in) + 3NG (h0 term) + 3NG (out) + sum(3L^2 + 3L)] -- the residual q rows, the keep mask and the
+    flag bytes the kernel also moves are NOT counted."""
     from mmdfn_b200 import ops
-    from mmdfn_b200._lib import call, ptr, stream
+    from mmdfn_b200._lib import call, ptr, ptr_table, query, stream
     lengths = [UTT] * n_dialogues
     geom = ops.DialogGeom(lengths, dev)
     N, G = geom.N, 100
-    alg_bytes = 4 * (3 * N * G + 3 * N * G + sum(3 * L * L + 3 * L for L in lengths))     # z in, hi out, A_hat blocks + diagonals
-    copies = max(2, int(300e6 // alg_bytes) + 1)
+    n3 = 3 * N
+    alg_bytes = 4 * (3 * n3 * G + sum(3 * L * L + 3 * L for L in lengths))
+    moved_bytes = alg_bytes + 4 * n3 * G + 2 * n3 * G          # + q rows + mask and flag bytes
+    copies = max(2, int(300e6 // moved_bytes) + 1)
     g = torch.Generator(device=dev).manual_seed(0)
     blk = [torch.rand(geom.nblk, device=dev, generator=g) / UTT for _ in range(copies)]
     dg = [torch.rand(3, N, device=dev, generator=g) / UTT for _ in range(copies)]
-    z = [torch.randn(3 * N, G, device=dev, generator=g) for _ in range(copies)]
-    y = [torch.empty(3 * N, G, device=dev) for _ in range(copies)]
+    z = [torch.randn(n3, G, device=dev, generator=g) for _ in range(copies)]
+    r = [torch.randn(n3, G, device=dev, generator=g) for _ in range(copies)]
+    q = [torch.randn(n3, G, device=dev, generator=g) for _ in range(copies)]
+    mk = [(torch.rand(n3, G, device=dev, generator=g) > DROPOUT).to(torch.uint8) for _ in range(copies)]
+    y = [torch.empty(n3, G, device=dev) for _ in range(copies)]
+    fl = [torch.empty(n3, G, device=dev, dtype=torch.uint8) for _ in range(copies)]
+    W = [torch.randn(200, 100, device=dev, generator=g) * 0.1]
+    img_n = query("mmdfn_gcn_layer_img_floats")
+    mtop, mbot = torch.empty(100, 100, device=dev), torch.empty(100, 100, device=dev)
+    img_f, img_b = torch.empty(img_n, device=dev), torch.empty(img_n, device=dev)
+    call("mmdfn_gcn_layer_prep", 1, ptr_table(W), 0.5, 0.2, ptr(mtop), ptr(mbot), ptr(img_f), ptr(img_b), stream())
+
     def launch(i):
-        call("mmdfn_adj_spmm", *geom.args(), ptr(blk[i]), ptr(dg[i]), ptr(z[i]), G, ptr(y[i]), stream())
+        call("mmdfn_gcn_layer_fwd", *geom.args(), ptr(blk[i]), ptr(dg[i]), ptr(z[i]), ptr(img_f), ptr(r[i]), G, ptr(q[i]),
+             ptr(mk[i], torch.uint8), 1.0 / (1.0 - DROPOUT), ptr(fl[i], torch.uint8), ptr(y[i]), G, stream())
 
     half = alg_bytes // 8
     src = [torch.empty(half, device=dev) for _ in range(copies)]
@@ -308,16 +328,17 @@ def roofline_graph_conv(dev, n_dialogues=DIALOGUES_PER_GPU):
     us_copy, _ = timed_us(launch_copy)
     peak, how = measured_peak_gbs()
     achieved = alg_bytes / (us * 1e-6) / 1e9
-    return {"kernel": "adj_spmm_tc_kernel (k6 graph-conv message aggregate hi = A_hat z; tcgen05 3xTF32, fp32-level accuracy)", "bound": "hbm",
+    return {"kernel": "gcn_layer_kernel<fwd> (fused GraphConvolution layer: tcgen05 3xTF32 aggregate hi = A_hat z chained with hi Mtop, "
+                      "+ h0 term, ReLU, dropout, + q in one launch; fp32-level accuracy)", "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel inside a training step
-            # (ncu --set full, profiles/r01_ncu_adj_spmm_tc_s2_final.csv: 7.76 MB read, 0 written -- z is partly L2-resident
-            # and the 3.84 MB of output stay in L2 for the consumer)
-            "traffic": 7761920 if n_dialogues == DIALOGUES_PER_GPU else None,
-            "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us, "peak_source": how,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel inside a training step, from the
+            # committed `ncu --set full` capture (profiles/README.md names the file); null until that capture exists
+            "traffic": NCU_TRAFFIC_BYTES if n_dialogues == DIALOGUES_PER_GPU else None,
+            "algorithmic_bytes_per_launch": alg_bytes, "bytes_moved_per_launch_incl_q_mask_flags": moved_bytes,
+            "us_per_launch": us, "peak_source": how,
             "same_bytes_copy_kernel": {"us_per_launch": us_copy, "frac": alg_bytes / (us_copy * 1e-6) / 1e9 / peak},
-            "note": "launch covers one GCN layer of the %dx100 shard; %d back-to-back launches (%s), operands rotated over "
-                    "%d copies (> L2)" % (n_dialogues, reps, mode, copies)}
+            "note": "launch covers one whole GCN layer (SURVEY 8d k6 bytes) of the %dx100 shard; %d back-to-back launches (%s), "
+                    "operands rotated over %d copies (> L2)" % (n_dialogues, reps, mode, copies)}
 
 
 def _claim_stdout():

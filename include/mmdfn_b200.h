@@ -137,6 +137,33 @@ int mmdfn_adj_spmm(int B, int N, int Lmax, const int* dia_off, const long long* 
 int mmdfn_adj_grad(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* dhi,
                    const float* z, int G, float* d_blk, float* d_diag, int accumulate, void* stream);
 
+/* ---- k6 fused: one launch per GraphConvolution layer (code/model_GCN.py:176-189 + the ReLU / dropout / "+= q" of the
+ * GCNII_lyc loop :469-472) for G = 100, any dialogue length -- tcgen05 aggregate chained with the weight product and
+ * the epilogue on chip (gcn_layer.cu).  With theta_l = ln(lamda/l + 1):
+ *   Mtop_l = theta_l W_l[0:100] + (1-theta_l)(1-alpha) I,   Mbot_l = theta_l W_l[100:200] + (1-theta_l) alpha I
+ *   u = (A_hat zin) Mtop_l + h0 Mbot_l   ==   theta [hi|h0] W + (1-theta)((1-alpha) hi + alpha h0)
+ * mmdfn_gcn_layer_prep builds, for K layers, mtop_all / mbot_all ((100, 100 K) row-major, column block l) and the
+ * pre-split tensor-core operand images img_f / img_b (K x mmdfn_gcn_layer_img_floats() floats: forward / transposed).
+ * The caller computes r = h0 Mbot_l (for all layers at once: R_all = h0 mbot_all, one mmdfn_gemm; ldr = 100 K).
+ * fwd : out = dropout(relu((A_hat zin) Mtop + r)) (+ q), flags (3N,100) bytes = [relu and keep]; zin / q row stride 100,
+ *       out row stride ldo, mask (3N,100) keep bytes or NULL.
+ * bwd : t_out = A_hat du (row stride ldt), out = t_out Mtop^T (+ add); du row stride ldu.  (dMtop = zin^T t_out.) */
+long long mmdfn_gcn_layer_img_floats(void);
+int mmdfn_gcn_layer_prep(int K, const float* const* convW, double lamda, double alpha, float* mtop_all, float* mbot_all,
+                         float* img_f, float* img_b, void* stream);
+int mmdfn_gcn_layer_fwd(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* adj_blk,
+                        const float* adj_diag, const float* zin, const float* wimg, const float* r, long long ldr,
+                        const float* q, const unsigned char* mask, float mask_scale, unsigned char* flags, float* out,
+                        long long ldo, void* stream);
+int mmdfn_gcn_layer_bwd(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* adj_blk,
+                        const float* adj_diag, const float* du, long long ldu, const float* wimg_t, float* t_out,
+                        long long ldt, const float* add, float* out, void* stream);
+/* timing aid (process-global, like mmdfn_adj_spmm_set_variant): 0 = 16-wide K chunks / 2 operand stages (default),
+ * 1 = 8-wide chunks / 3 stages.  Weight images must be (re)built by mmdfn_gcn_layer_prep under the same setting. */
+int mmdfn_gcn_layer_set_variant(int v);
+/* profiling aid: 256 x int64 device buffer receiving clock64() stamps of CTA (0,0) (NULL switches it off) */
+int mmdfn_gcn_layer_set_debug(long long* device_buf);
+
 /* ---- k6/k7/k8: GCNII_lyc stack (code/model_GCN.py:444-488, GraphConvolution :176-189, LSTM :466)
  * X (3N,200) -> F (3N,300) = [dropout(X) | z_K].  convW: K pointers to (200,100).  masks: keep bytes
  * (3N,200), (3N,100), (K,3N,100) or NULL. */
@@ -147,7 +174,7 @@ int mmdfn_gcn_stack_fwd(int B, int N, int Lmax, const int* dia_off, const long l
                         const float* w_hh, const float* b_ih, const float* b_hh, const unsigned char* mask_x,
                         const unsigned char* mask_h0, const unsigned char* mask_layers, float mask_scale, float* F,
                         float* ws, void* stream);
-long long mmdfn_gcn_stack_bwd_ws_floats(int n3);
+long long mmdfn_gcn_stack_bwd_ws_floats(int n3, int K);
 /* grads_zeroed != 0 (here and in mmdfn_head_bwd): every weight/bias gradient buffer was zero-filled by the caller
  * (one memset of a shared buffer) and is accumulated into -- no per-GEMM zero-init launches. */
 int mmdfn_gcn_stack_bwd(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* adj_blk,

@@ -64,7 +64,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = _T[res]
             fn.argtypes = [_T[c] for c in args]
-        if L.mmdfn_abi_version() != 1:
+        if L.mmdfn_abi_version() != 2:
             raise MMDFNError("libmmdfn_b200.so ABI version mismatch")
         _lib = L
     return _lib

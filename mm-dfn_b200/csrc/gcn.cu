@@ -12,14 +12,13 @@ constexpr int GG = 100;   // graph hidden size (graph_h, code/run_train_erc.py:3
 constexpr int GX = 200;   // graph input width
 constexpr int GF = 300;   // output row: [x (200) | z_K (100)]
 
-// per-layer saved activations, in floats per node row
+// per-layer saved activations, in floats per node row (the fused layer kernel of gcn_layer.cu keeps hi / u on chip)
 constexpr int SV_GATES = 0;      // 400: i f g o (activated)
 constexpr int SV_C = 400;        // 100
 constexpr int SV_H = 500;        // 100
-constexpr int SV_HI = 600;       // 100
-constexpr int SV_RD = 700;       // 100: dropout(relu(u))
-constexpr int SV_Z = 800;        // 100: z_{l+1}
-constexpr int SV_ROW = 900;
+constexpr int SV_Z = 600;        // 100: z_{l+1}
+constexpr int SV_FLAGS = 700;    // 25 floats = 100 bytes: [relu and keep] flags of the layer's output
+constexpr int SV_ROW = 728;      // rounded so that every region of every layer stays 16-byte aligned for any row count
 
 __global__ void lstm_fwd_kernel(i64 n, const float* __restrict__ pre, const float* __restrict__ c_prev,
                                 float* __restrict__ gates, float* __restrict__ c, float* __restrict__ h) {
@@ -57,31 +56,18 @@ __global__ void lstm_bwd_kernel(i64 n, const float* __restrict__ dh, const float
   dc_out[idx] = dc * f_;
 }
 
-// u = theta*u1 + (1-theta)*((1-alpha)*hi + alpha*h0); rd = dropout(relu(u)); z = rd (+ q)
-__global__ void gcn_epi_fwd_kernel(i64 n, const float* __restrict__ u1, const float* __restrict__ hi,
-                                   const float* __restrict__ h0, const float* __restrict__ q,
-                                   const unsigned char* __restrict__ mask, float scale, float theta, float omt,
-                                   float alpha, float oma, float* __restrict__ rd, float* __restrict__ z) {
-  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  const float r = oma * hi[idx] + alpha * h0[idx];
-  const float u = theta * u1[idx] + omt * r;
-  float v = fmaxf(u, 0.f);
-  if (mask) v = mask[idx] ? v * scale : 0.f;
-  rd[idx] = v;
-  z[idx] = q ? v + q[idx] : v;
-}
-
-// du = dz * [rd > 0] * scale ; du1 = theta*du ; dhi = (1-theta)(1-alpha) du ; dh0 += (1-theta) alpha du
-__global__ void gcn_epi_bwd_kernel(i64 n, const float* __restrict__ dz, const float* __restrict__ rd, float scale,
-                                   float theta, float omt, float alpha, float oma, float* __restrict__ du1,
-                                   float* __restrict__ dhi, float* __restrict__ dh0) {
-  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  const float du = rd[idx] > 0.f ? dz[idx] * scale : 0.f;
-  du1[idx] = theta * du;
-  dhi[idx] = omt * oma * du;
-  dh0[idx] += omt * alpha * du;
+// du[r, 0:100] (ld ldu) = flags ? dz[r, 0:100] (ld ldz) * scale : 0     (through dropout and ReLU of the layer output)
+__global__ void gcn_du_kernel(i64 rows, const float* __restrict__ dz, i64 ldz, const unsigned char* __restrict__ flags,
+                              float scale, float* __restrict__ du, i64 ldu) {
+  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;          // one float4 per thread
+  if (idx >= rows * (GG / 4)) return;
+  const i64 r = idx / (GG / 4);
+  const int c4 = (int)(idx - r * (GG / 4));
+  const float4 g = *(reinterpret_cast<const float4*>(dz + r * ldz) + c4);
+  const uint32_t f = *(reinterpret_cast<const uint32_t*>(flags + r * GG) + c4);
+  *(reinterpret_cast<float4*>(du + r * ldu) + c4) =
+      make_float4((f & 0xFFu) ? g.x * scale : 0.f, (f & 0xFF00u) ? g.y * scale : 0.f, (f & 0xFF0000u) ? g.z * scale : 0.f,
+                  (f & 0xFF000000u) ? g.w * scale : 0.f);
 }
 
 // dst[r, 0:cols] (ld dld) = src[r, 0:cols] (ld sld) [* mask*scale]
@@ -121,22 +107,36 @@ __global__ void x_bwd_kernel(i64 rows, const float* __restrict__ dF, const float
   dX[idx] = v;
 }
 
-// y += x
-__global__ void axpy_kernel(i64 n, const float* __restrict__ x, float* __restrict__ y) {
-  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < n) y[idx] += x[idx];
-}
-
 static inline unsigned nblk(i64 n) { return (unsigned)ceil_div64(n, 256); }
 
 }  // namespace mmdfn
 
 using namespace mmdfn;
 
-extern "C" long long mmdfn_gcn_stack_ws_floats(int n3, int K) {
-  // h0 (100) | z0 (100) | zeros (100) | K x SV_ROW | scratch: pre (400) + u1 (100)
-  return (i64)n3 * (300 + (i64)K * SV_ROW + 500);
+// workspace layout of the forward (floats; every region starts 16-byte aligned):
+//   h0 (n3 x 100) | z0 (n3 x 100) | zeros (n3 x 100) | R_all (n3 x 100 K) | K x [layer: n3 x SV_ROW] | pre (n3 x 400)
+//   | Mtop_all (100 x 100 K) | Mbot_all (100 x 100 K) | img_f (K images) | img_b (K images)
+struct StackWs {
+  i64 h0, z0, zeros, r_all, layers, pre, mtop, mbot, img_f, img_b, total;
+};
+static StackWs stack_ws(i64 n3, int K) {
+  StackWs w;
+  i64 o = 0;
+  w.h0 = o; o += n3 * GG;
+  w.z0 = o; o += n3 * GG;
+  w.zeros = o; o += n3 * GG;
+  w.r_all = o; o += n3 * GG * K;
+  w.layers = o; o += n3 * SV_ROW * K;
+  w.pre = o; o += n3 * 4 * GG;
+  w.mtop = o; o += (i64)GG * GG * K;
+  w.mbot = o; o += (i64)GG * GG * K;
+  w.img_f = o; o += gcn_layer_img_floats() * K;
+  w.img_b = o; o += gcn_layer_img_floats() * K;
+  w.total = o;
+  return w;
 }
+
+extern "C" long long mmdfn_gcn_stack_ws_floats(int n3, int K) { return stack_ws(n3, K < 0 ? 0 : K).total; }
 
 extern "C" int mmdfn_gcn_stack_fwd(int B, int N, int Lmax, const int* dia_off, const long long* blk_off,
                                    const float* adj_blk, const float* adj_diag, const float* X, int K,
@@ -152,12 +152,14 @@ extern "C" int mmdfn_gcn_stack_fwd(int B, int N, int Lmax, const int* dia_off, c
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const i64 n3 = (i64)3 * N;
-  float* h0 = ws;
-  float* z0 = h0 + n3 * GG;
-  float* zeros = z0 + n3 * GG;
-  float* layers = zeros + n3 * GG;
-  float* pre = layers + (i64)K * n3 * SV_ROW;
-  float* u1 = pre + n3 * 4 * GG;
+  const StackWs w = stack_ws(n3, K);
+  float* h0 = ws + w.h0;
+  float* z0 = ws + w.z0;
+  float* zeros = ws + w.zeros;
+  float* r_all = ws + w.r_all;
+  float* layers = ws + w.layers;
+  float* pre = ws + w.pre;
+  const i64 ldk = (i64)GG * K;
   // x_d = dropout(X) stored straight into F[:, 0:200]                           (model_GCN.py:453,483)
   copy2d_mask_kernel<<<nblk(n3 * GX), 256, 0, st>>>(n3, GX, X, GX, mask_x, mask_scale, F, GF);
   MMDFN_LAUNCH_CHECK();
@@ -165,7 +167,16 @@ extern "C" int mmdfn_gcn_stack_fwd(int B, int N, int Lmax, const int* dia_off, c
   MMDFN_TRY(gemm(false, true, (int)n3, GG, GX, 1.f, F, GF, W0, GX, 0.f, h0, GG, b0, 1, st));
   copy2d_mask_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3, GG, h0, GG, mask_h0, mask_scale, z0, GG);   // (:456)
   MMDFN_LAUNCH_CHECK();
-  MMDFN_TRY(fill_zero(zeros, (size_t)n3 * GG * sizeof(float), st));
+  if (K == 0) {
+    copy2d_mask_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3, GG, z0, GG, nullptr, 1.f, F + GX, GF);    // (:482-483)
+    MMDFN_LAUNCH_CHECK();
+    return 0;
+  }
+  if (reason_flag) MMDFN_TRY(fill_zero(zeros, (size_t)n3 * GG * sizeof(float), st));
+  // folded layer weights (theta / alpha mixes inside the operands) and their pre-split tensor-core images, then the
+  // layer-invariant half of every layer in ONE product: R_all = h0 [Mbot_1 | .. | Mbot_K]
+  MMDFN_TRY(gcn_layer_prep(K, convW, lamda, alpha, ws + w.mtop, ws + w.mbot, ws + w.img_f, ws + w.img_b, st));
+  MMDFN_TRY(gemm(false, false, (int)n3, (int)ldk, GG, 1.f, h0, GG, ws + w.mbot, ldk, 0.f, r_all, ldk, nullptr, 0, st));
   const float* zl = z0;
   const float* hl = zeros;
   const float* cl = zeros;
@@ -174,9 +185,8 @@ extern "C" int mmdfn_gcn_stack_fwd(int B, int N, int Lmax, const int* dia_off, c
     float* gates = sv + n3 * SV_GATES;
     float* c = sv + n3 * SV_C;
     float* h = sv + n3 * SV_H;
-    float* hi = sv + n3 * SV_HI;
-    float* rd = sv + n3 * SV_RD;
     float* z = sv + n3 * SV_Z;
+    unsigned char* flags = reinterpret_cast<unsigned char*>(sv + n3 * SV_FLAGS);
     const float* agg_in = zl;
     if (reason_flag) {
       MMDFN_TRY(gemm(false, true, (int)n3, 4 * GG, GG, 1.f, zl, GG, w_ih, GG, 0.f, pre, 4 * GG, b_ih, 0, st));
@@ -186,26 +196,23 @@ extern "C" int mmdfn_gcn_stack_fwd(int B, int N, int Lmax, const int* dia_off, c
       MMDFN_LAUNCH_CHECK();
       agg_in = h;
     }
-    MMDFN_TRY(adj_spmm(B, N, Lmax, dia_off, (const i64*)blk_off, adj_blk, adj_diag, agg_in, GG, hi, st));
-    MMDFN_TRY(gemm(false, false, (int)n3, GG, GG, 1.f, hi, GG, convW[l], GG, 0.f, u1, GG, nullptr, 0, st));
-    MMDFN_TRY(gemm(false, false, (int)n3, GG, GG, 1.f, h0, GG, convW[l] + GG * GG, GG, 1.f, u1, GG, nullptr, 0, st));
-    const double theta_d = log(lamda / (double)(l + 1) + 1.0);      // python float math (model_GCN.py:177)
-    const float theta = (float)theta_d, omt = (float)(1.0 - theta_d);
+    // one launch: aggregate -> x Mtop -> + R -> ReLU -> dropout -> (+ q); the last layer writes F[:, 200:300] directly
     const unsigned char* mk = mask_layers ? mask_layers + (i64)l * n3 * GG : nullptr;
-    gcn_epi_fwd_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3 * GG, u1, hi, h0, reason_flag ? zl : nullptr, mk, mask_scale,
-                                                      theta, omt, (float)alpha, (float)(1.0 - alpha), rd, z);
-    MMDFN_LAUNCH_CHECK();
+    const bool last = (l == K - 1);
+    MMDFN_TRY(gcn_layer_fwd(B, N, Lmax, dia_off, (const i64*)blk_off, adj_blk, adj_diag, agg_in,
+                            ws + w.img_f + (i64)l * gcn_layer_img_floats(), r_all + (i64)l * GG, ldk,
+                            reason_flag ? zl : nullptr, mk, mask_scale, flags, last ? F + GX : z, last ? GF : GG, st));
     zl = z;
     if (reason_flag) { hl = h; cl = c; }
   }
-  copy2d_mask_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3, GG, zl, GG, nullptr, 1.f, F + GX, GF);       // (:482-483)
-  MMDFN_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" long long mmdfn_gcn_stack_bwd_ws_floats(int n3) {
-  // dz (100) dh0 (100) dhc (100) dcc (100) du1 (100) dhi (100) dh (100) dgates (400) dxd (200)
-  return (i64)n3 * 1300;
+// backward workspace: dz dh0 dhc dcc dh dhi (n3 x 100 each) | dgates (n3 x 400) | dxd (n3 x 200) | DU_all (n3 x 100 K)
+// | T_all (n3 x 100 K) | dMtop_all (100 x 100 K) | dMbot_all (100 x 100 K)
+extern "C" long long mmdfn_gcn_stack_bwd_ws_floats(int n3, int K) {
+  if (K < 0) K = 0;
+  return (i64)n3 * (1200 + 2 * (i64)GG * K) + 2 * (i64)GG * GG * K;
 }
 
 // dW pointers receive "=" (not "+="); d_adj_blk/d_adj_diag (nullable pair) receive the true
@@ -226,30 +233,34 @@ extern "C" int mmdfn_gcn_stack_bwd(int B, int N, int Lmax, const int* dia_off, c
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const i64 n3 = (i64)3 * N;
-  const float* h0 = ws_fwd;
-  const float* z0 = h0 + n3 * GG;
-  const float* zeros = z0 + n3 * GG;
-  const float* layers = zeros + n3 * GG;
+  const StackWs w = stack_ws(n3, K);
+  const float* h0 = ws_fwd + w.h0;
+  const float* z0 = ws_fwd + w.z0;
+  const float* zeros = ws_fwd + w.zeros;
+  const float* layers = ws_fwd + w.layers;
+  const float* mtop_all = ws_fwd + w.mtop;
+  const float* mbot_all = ws_fwd + w.mbot;
+  const float* img_b = ws_fwd + w.img_b;
+  const i64 ldk = (i64)GG * K;
   float* dz = ws;
   float* dh0 = dz + n3 * GG;
   float* dhc = dh0 + n3 * GG;
   float* dcc = dhc + n3 * GG;
-  float* du1 = dcc + n3 * GG;
-  float* dhi = du1 + n3 * GG;
-  float* dh = dhi + n3 * GG;
-  float* dgates = dh + n3 * GG;
+  float* dh = dcc + n3 * GG;
+  float* dhi = dh + n3 * GG;
+  float* dgates = dhi + n3 * GG;
   float* dxd = dgates + n3 * 4 * GG;
+  float* du_all = dxd + n3 * GX;
+  float* t_all = du_all + n3 * ldk;
+  float* dmtop_all = t_all + n3 * ldk;
+  float* dmbot_all = dmtop_all + (i64)GG * ldk;
   const float scale = mask_layers ? mask_scale : 1.f;
   // dz_K = dF[:, 200:300]
   copy2d_mask_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3, GG, dF + GX, GF, nullptr, 1.f, dz, GG);
   MMDFN_LAUNCH_CHECK();
-  MMDFN_TRY(fill_zero(dh0, (size_t)n3 * GG * sizeof(float), st));
+  if (K == 0) MMDFN_TRY(fill_zero(dh0, (size_t)n3 * GG * sizeof(float), st));
+  else MMDFN_TRY(fill_zero(dmtop_all, (size_t)2 * GG * ldk * sizeof(float), st));      // dMtop_all | dMbot_all: split-K targets
   const float gb = grads_zeroed ? 1.f : 0.f;     // caller pre-zeroed every gradient buffer: accumulate, no zero-init launches
-  if (reason_flag && K == 0 && !grads_zeroed) {
-    MMDFN_TRY(fill_zero(dw_ih, 4 * GG * GG * sizeof(float), st));
-    MMDFN_TRY(fill_zero(dw_hh, 4 * GG * GG * sizeof(float), st));
-    MMDFN_TRY(fill_zero(db_ih, 4 * GG * sizeof(float), st));
-  }
   bool have_carry = false;     // dhc / dcc valid (gradient flowing into h_{l+1}, c_{l+1} from layer l+1)
   bool first_rnn = true;
   for (int l = K - 1; l >= 0; l--) {
@@ -257,36 +268,29 @@ extern "C" int mmdfn_gcn_stack_bwd(int B, int N, int Lmax, const int* dia_off, c
     const float* gates = sv + n3 * SV_GATES;
     const float* c = sv + n3 * SV_C;
     const float* h = sv + n3 * SV_H;
-    const float* hi = sv + n3 * SV_HI;
-    const float* rd = sv + n3 * SV_RD;
+    const unsigned char* flags = reinterpret_cast<const unsigned char*>(sv + n3 * SV_FLAGS);
     const float* zprev = l > 0 ? layers + (i64)(l - 1) * n3 * SV_ROW + n3 * SV_Z : z0;
     const float* hprev = l > 0 ? layers + (i64)(l - 1) * n3 * SV_ROW + n3 * SV_H : zeros;
     const float* cprev = l > 0 ? layers + (i64)(l - 1) * n3 * SV_ROW + n3 * SV_C : zeros;
-    const double theta_d = log(lamda / (double)(l + 1) + 1.0);
-    const float theta = (float)theta_d, omt = (float)(1.0 - theta_d);
-    gcn_epi_bwd_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3 * GG, dz, rd, scale, theta, omt, (float)alpha,
-                                                      (float)(1.0 - alpha), du1, dhi, dh0);
-    MMDFN_LAUNCH_CHECK();
-    // dhi += du1 Wtop^T ; dh0 += du1 Wbot^T ; dW = [hi|h0]^T du1
-    MMDFN_TRY(gemm(false, true, (int)n3, GG, GG, 1.f, du1, GG, convW[l], GG, 1.f, dhi, GG, nullptr, 0, st));
-    MMDFN_TRY(gemm(false, true, (int)n3, GG, GG, 1.f, du1, GG, convW[l] + GG * GG, GG, 1.f, dh0, GG, nullptr, 0, st));
-    MMDFN_TRY(gemm(true, false, GG, GG, (int)n3, 1.f, hi, GG, du1, GG, gb, dconvW[l], GG, nullptr, 0, st));
-    MMDFN_TRY(gemm(true, false, GG, GG, (int)n3, 1.f, h0, GG, du1, GG, gb, dconvW[l] + GG * GG, GG, nullptr, 0, st));
     const float* agg_in = reason_flag ? h : zprev;
-    if (d_adj_blk)
+    float* du = du_all + (i64)l * GG;             // column block l of DU_all (row stride 100 K)
+    float* tl = t_all + (i64)l * GG;
+    // du = dz * [relu and keep] * scale
+    gcn_du_kernel<<<nblk(n3 * (GG / 4)), 256, 0, st>>>(n3, dz, GG, flags, scale, du, ldk);
+    MMDFN_LAUNCH_CHECK();
+    // one launch: t = A_hat du (kept: dMtop = agg_in^T t) and d agg_in = t Mtop^T (+ the gradient carried into h from
+    // layer l+1's recurrent product)
+    MMDFN_TRY(gcn_layer_bwd(B, N, Lmax, dia_off, (const i64*)blk_off, adj_blk, adj_diag, du, ldk,
+                            img_b + (i64)l * gcn_layer_img_floats(), tl, ldk,
+                            (reason_flag && have_carry) ? dhc : nullptr, reason_flag ? dh : dz, st));
+    MMDFN_TRY(gemm(true, false, GG, GG, (int)n3, 1.f, agg_in, GG, tl, ldk, 1.f, dmtop_all + (i64)l * GG, ldk, nullptr, 0, st));
+    if (d_adj_blk) {
+      // dhi = du Mtop^T, dA_hat += sym(dhi agg_in^T)
+      MMDFN_TRY(gemm(false, true, (int)n3, GG, GG, 1.f, du, ldk, mtop_all + (i64)l * GG, ldk, 0.f, dhi, GG, nullptr, 0, st));
       MMDFN_TRY(adj_grad_accum(B, N, Lmax, dia_off, (const i64*)blk_off, dhi, agg_in, GG, d_adj_blk, d_adj_diag,
                                l != K - 1, st));
-    if (!reason_flag) {
-      // z_l -> (aggregate) only: dz_{l} = A_hat dhi
-      MMDFN_TRY(adj_spmm(B, N, Lmax, dia_off, (const i64*)blk_off, adj_blk, adj_diag, dhi, GG, dz, st));
-      continue;
     }
-    MMDFN_TRY(adj_spmm(B, N, Lmax, dia_off, (const i64*)blk_off, adj_blk, adj_diag, dhi, GG, dh, st));
-    if (have_carry) {
-      // dh += dhc  (gradient into h_{l+1} from layer l+1's recurrent GEMM)
-      axpy_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3 * GG, dhc, dh);
-      MMDFN_LAUNCH_CHECK();
-    }
+    if (!reason_flag) continue;                  // dz now holds dz_l = A_hat-path gradient only (no residual, no gate)
     lstm_bwd_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3, dh, have_carry ? dcc : nullptr, gates, c, cprev, dgates, dcc);
     MMDFN_LAUNCH_CHECK();
     // dz_l = dz_{l+1} (residual +q) + dgates W_ih ; dhc = dgates W_hh
@@ -303,11 +307,17 @@ extern "C" int mmdfn_gcn_stack_bwd(int B, int N, int Lmax, const int* dia_off, c
     first_rnn = false;
     have_carry = true;
   }
+  if (K > 0) {
+    // the h0 half of every layer at once: dh0 = DU_all Mbot_all^T ; dMbot_all = h0^T DU_all ; then dW_l = theta_l [dMtop_l ; dMbot_l]
+    MMDFN_TRY(gemm(false, true, (int)n3, GG, (int)ldk, 1.f, du_all, ldk, mbot_all, ldk, 0.f, dh0, GG, nullptr, 0, st));
+    MMDFN_TRY(gemm(true, false, GG, (int)ldk, (int)n3, 1.f, h0, GG, du_all, ldk, 1.f, dmbot_all, ldk, nullptr, 0, st));
+    MMDFN_TRY(gcn_layer_unfold(K, dconvW, lamda, dmtop_all, dmbot_all, grads_zeroed, st));
+  }
   if (reason_flag && db_hh && K > 0) {
     MMDFN_CUDA(cudaMemcpyAsync(db_hh, db_ih, 4 * GG * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   // through z0 = dropout(h0), h0 = relu(x_d W0^T + b0)
-  float* dpre = du1;
+  float* dpre = dhi;
   h0_bwd_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3 * GG, dh0, dz, mask_h0, mask_scale, h0, dpre);
   MMDFN_LAUNCH_CHECK();
   MMDFN_TRY(gemm(true, false, GG, GX, (int)n3, 1.f, dpre, GG, F, GF, gb, dW0, GX, nullptr, 0, st));

@@ -28,4 +28,22 @@ int adj_spmm_tc_long(int B, int N, int Lmax, const int* dia_off, const i64* blk_
 int adj_grad_accum(int B, int N, int Lmax, const int* dia_off, const i64* blk_off, const float* dhi,
                    const float* z, int G, float* p_blk, float* p_diag, int accumulate, cudaStream_t st);
 
+
+// ---- fused graph-conv layer (gcn_layer.cu): aggregate -> x folded weight -> fused epilogue, one launch per layer ----
+long long gcn_layer_img_floats();
+// folded matrices Mtop_l / Mbot_l (column blocks of two (100, 100 K) matrices) and the pre-split phase-B operand images
+int gcn_layer_prep(int K, const float* const* convW, double lamda, double alpha, float* mtop_all, float* mbot_all,
+                   float* img_f, float* img_b, cudaStream_t st);
+// dconvW[l] (=, or += when accumulate) theta_l [dMtop_l ; dMbot_l]
+int gcn_layer_unfold(int K, float* const* dconvW, double lamda, const float* dmtop_all, const float* dmbot_all,
+                     int accumulate, cudaStream_t st);
+// out = dropout(relu((A_hat zin) Mtop + r)) (+ q); flags = [relu and keep]
+int gcn_layer_fwd(int B, int N, int Lmax, const int* dia_off, const i64* blk_off, const float* adj_blk,
+                  const float* adj_diag, const float* zin, const float* wimg, const float* r, i64 ldr, const float* q,
+                  const unsigned char* mask, float scale, unsigned char* flags, float* out, i64 ldo, cudaStream_t st);
+// t_out = A_hat du ; out = t_out Mtop^T (+ add)
+int gcn_layer_bwd(int B, int N, int Lmax, const int* dia_off, const i64* blk_off, const float* adj_blk,
+                  const float* adj_diag, const float* du, i64 ldu, const float* wimg_t, float* t_out, i64 ldt,
+                  const float* add, float* out, cudaStream_t st);
+
 }  // namespace mmdfn

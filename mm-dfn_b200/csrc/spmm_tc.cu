@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) adj_spmm_tc_kernel(SpmmTcArgs p
   if (tid == 0) {
     for (int s = 0; s < 2; s++) {
       umma::mbar_init(&bar_free[s], 1);
-      umma::mbar_init(&bar_full[s], ST_CONV);
+      umma::mbar_init(&bar_full[s], ST_CONV / 32);
     }
     for (int c = 0; c < ST_NCH; c++) umma::mbar_init(&bar_z[c], 1);
     umma::fence_barrier_init();
@@ -217,8 +217,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) adj_spmm_tc_kernel(SpmmTcArgs p
           *reinterpret_cast<float4*>(st + 2 * ST_A_PART + ST_B_PART + o) = l;
         }
       }
-      umma::fence_proxy_async_smem();
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(&bar_full[s])) : "memory");
+      umma::warp_arrive_full(&bar_full[s]);
       ST_STAMP();                                             // converted
     }
   }
@@ -256,8 +255,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) adj_spmm_tc_kernel(SpmmTcArgs p
     for (int cb = cb_begin; cb < cb_end; cb += 16) {
       if (cb >= ST_G) break;
       float v[16], w[16];
-      umma::tmem_ld16(taddr + cb, v);
-      umma::tmem_ld16(taddr + ST_CORR + cb, w);
+      umma::tmem_ld16x2(taddr + cb, taddr + ST_CORR + cb, v, w);
 #pragma unroll
       for (int q4 = 0; q4 < 16; q4 += 4) {
         if (cb + q4 < ST_G)                                   // G = 100: the last chunk stops after one quad

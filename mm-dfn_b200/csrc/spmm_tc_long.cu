@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(SL_THREADS, 2) adj_spmm_tc_long_kernel(SpmmLon
   if (tid == 0) {
     for (int s = 0; s < 2; s++) {
       umma::mbar_init(&bar_free[s], 1);
-      umma::mbar_init(&bar_full[s], SL_CONV);
+      umma::mbar_init(&bar_full[s], SL_CONV / 32);
     }
     for (int s = 0; s < SL_ZR; s++) umma::mbar_init(&bar_z[s], 1);
     umma::fence_barrier_init();
@@ -207,8 +207,7 @@ __global__ void __launch_bounds__(SL_THREADS, 2) adj_spmm_tc_long_kernel(SpmmLon
             *reinterpret_cast<float4*>(st + 2 * SL_A_PART + SL_B_PART + o) = l;
           }
         }
-        umma::fence_proxy_async_smem();
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(&bar_full[s])) : "memory");
+        umma::warp_arrive_full(&bar_full[s]);
       }
     }
   }
@@ -241,8 +240,7 @@ __global__ void __launch_bounds__(SL_THREADS, 2) adj_spmm_tc_long_kernel(SpmmLon
     for (int cb = cb_begin; cb < cb_end; cb += 16) {
       if (cb >= SL_G) break;
       float v[16], w[16];
-      umma::tmem_ld16(taddr + cb, v);
-      umma::tmem_ld16(taddr + SL_CORR + cb, w);
+      umma::tmem_ld16x2(taddr + cb, taddr + SL_CORR + cb, v, w);
 #pragma unroll
       for (int q4 = 0; q4 < 16; q4 += 4) {
         if (cb + q4 < SL_G)

@@ -60,6 +60,39 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// two 16-column loads (main accumulator + correction accumulator) in flight together, ONE wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr_a, uint32_t taddr_b, float (&v)[16], float (&w)[16]) {
+  uint32_t r[16], q[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr_a)
+      : "memory");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(taddr_b)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    v[i] = __uint_as_float(r[i]);
+    w[i] = __uint_as_float(q[i]);
+  }
+}
+
+// "stage full" hand-off of a converter warp: every lane makes its generic-proxy writes visible to the async proxy, the
+// warp converges, ONE lane arrives (barrier initialised with the number of converter WARPS) -- 8 arrivals per stage
+// instead of 256 serialized shared-memory atomics
+__device__ __forceinline__ void warp_arrive_full(uint64_t* bar) {
+  fence_proxy_async_smem();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0)
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---- descriptors ----------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_NONE, K-major canonical layout: an operand tile is a grid of
 // 8-row x 16-byte "core matrices" (128 contiguous bytes each); `lbo` = byte distance between the two

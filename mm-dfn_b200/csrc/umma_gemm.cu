@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(UG_ALL_THREADS, BN <= 128 ? 2 : 1) umma_gemm_k
   constexpr int UG_RAW_STAGE = LY::RAW_STAGE, UG_CORR_COL = LY::CORR_COL, UG_TMEM_COLS = LY::TMEM_COLS, NPB = LY::NPB;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_free[UG_STAGES];   // tensor core -> converters: stage may be overwritten
-  __shared__ __align__(8) uint64_t bar_full[UG_STAGES];   // converters -> issuer: stage holds chunk c (256 arrivals)
+  __shared__ __align__(8) uint64_t bar_full[UG_STAGES];   // converters -> issuer: stage holds chunk c (one arrival per converter warp)
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(UG_ALL_THREADS, BN <= 128 ? 2 : 1) umma_gemm_k
 #pragma unroll
     for (int s = 0; s < UG_STAGES; s++) {
       umma::mbar_init(&bar_free[s], 1);
-      umma::mbar_init(&bar_full[s], UG_THREADS);
+      umma::mbar_init(&bar_full[s], UG_THREADS / 32);
     }
     umma::fence_barrier_init();
   }
@@ -328,9 +328,8 @@ __global__ void __launch_bounds__(UG_ALL_THREADS, BN <= 128 ? 2 : 1) umma_gemm_k
       for (int i = 0; i < NPB; i++) ob.convert(i, vb[i], st + 2 * UG_A_PART, st + 2 * UG_A_PART + UG_B_PART);
     }
     UG_STAMP();                                           // [4] converted + stored
-    umma::fence_proxy_async_smem();                       // my generic-proxy writes -> visible to the tensor core
-    UG_STAMP();                                           // [5] fenced
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(&bar_full[s])) : "memory");
+    UG_STAMP();                                           // [5] before the hand-off
+    umma::warp_arrive_full(&bar_full[s]);                 // fence (generic -> async proxy), converge, one arrival per warp
     ring_r = (ring_r + 1 == UG_DEPTH) ? 0 : ring_r + 1;
     if (++s == UG_STAGES) { s = 0; free_parity ^= 1; }
   }
@@ -384,8 +383,7 @@ __global__ void __launch_bounds__(UG_ALL_THREADS, BN <= 128 ? 2 : 1) umma_gemm_k
     fetch_c(cb + 16);
     if (nchunks > 0) {
       float w[16];
-      umma::tmem_ld16(taddr + cb, v);
-      umma::tmem_ld16(taddr + UG_CORR_COL + cb, w);
+      umma::tmem_ld16x2(taddr + cb, taddr + UG_CORR_COL + cb, v, w);
 #pragma unroll
       for (int q = 0; q < 16; q++) v[q] += w[q];
     } else {

@@ -541,7 +541,7 @@ class GCNStackFn(torch.autograd.Function):
         dW0, db0 = views[0].view(100, 200), views[1]
         dw_ih, dw_hh, db_ih, db_hh = views[2].view(400, 100), views[3].view(400, 100), views[4], views[5]
         dconv = [v.view(200, 100) for v in views[6:]]
-        wsb = _empty((query("mmdfn_gcn_stack_bwd_ws_floats", n3),), dev)
+        wsb = _empty((query("mmdfn_gcn_stack_bwd_ws_floats", n3, K),), dev)
         tab = ptr_table(convW) if K > 0 else None
         dtab = ptr_table(dconv) if K > 0 else None
         call("mmdfn_gcn_stack_bwd", *geom.args(), ptr(adj_blk), ptr(adj_diag), K, reason_flag, lamda, alpha, ptr(W0),

@@ -33,11 +33,8 @@ def ref_code_dir(root=None):
 
 
 def ref_data_dir(root=None):
-    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__))) if root is None else root
-    for p in (os.path.join(here, "baseline", "_ref", "data"), "/root/reference/data"):
-        if os.path.exists(os.path.join(p, "iemocap", "IEMOCAP_features.pkl")):
-            return p
-    return None
+    """directory holding the reference's feature pickles (build container only: they are not staged)"""
+    return "/root/reference/data" if os.path.exists("/root/reference/data/iemocap/IEMOCAP_features.pkl") else None
 
 
 def install(code_dir=None):

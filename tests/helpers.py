@@ -43,47 +43,48 @@ def model_shapes(d_text, d_audio, d_visual, S, C, K):
     return out
 
 
-def staged_pickle(rel):
-    """path of a reference feature pickle staged under baseline/_ref/data (git-ignored; __graft_entry__.build() copies
-    it from /root/reference; it travels to the GPU box with the snapshot) or None"""
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for base in (os.path.join(root, "baseline", "_ref", "data"), "/root/reference/data"):
-        p = os.path.join(base, rel)
-        if os.path.exists(p):
-            return p
-    return None
-
-
-_PKL = {}
+_STAGED = {}
 
 
 def iemocap_batch(vids):
-    """the reference's collate of these IEMOCAP dialogues (code/dataloader.py:18-34): time-major zero-padded features,
-    one-hot qmask ('M' -> [1,0]), umask"""
-    import pickle
-    path = staged_pickle("iemocap/IEMOCAP_features.pkl")
-    if path is None:
+    """the reference's collate of these IEMOCAP test dialogues (code/dataloader.py:18-34): time-major zero-padded
+    features, one-hot qmask ('M' -> [1,0]), umask.  Raw features come from baseline/_ref/data/iemocap_test_dialogues.npz
+    (git-ignored; written by __graft_entry__.stage_reference() from the reference's pickle; travels to the GPU box) or
+    straight from the pickle when /root/reference exists.  None when neither is there."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    npz = os.path.join(root, "baseline", "_ref", "data", "iemocap_test_dialogues.npz")
+    pkl = "/root/reference/data/iemocap/IEMOCAP_features.pkl"
+    if "src" not in _STAGED:
+        if os.path.exists(npz):
+            z = np.load(npz, allow_pickle=False)
+            _STAGED["src"] = lambda kind, v: z[kind + "::" + v]
+        elif os.path.exists(pkl):
+            import pickle
+            ids, spk, labels, text, audio, visual = pickle.load(open(pkl, "rb"), encoding="latin1")[:6]
+            tab = {"text": text, "audio": audio, "visual": visual, "label": labels}
+            _STAGED["src"] = lambda kind, v: (np.array([0 if x == "M" else 1 for x in spk[v]]) if kind == "spk"
+                                              else np.asarray(tab[kind][v], np.float32 if kind != "label" else np.int64))
+        else:
+            _STAGED["src"] = None
+    src = _STAGED["src"]
+    if src is None:
         return None
-    if path not in _PKL:
-        _PKL[path] = pickle.load(open(path, "rb"), encoding="latin1")
-    ids, spk, labels, text, audio, visual = _PKL[path][:6]
-    lengths = [len(labels[v]) for v in vids]
+    lengths = [len(src("label", v)) for v in vids]
     T, B = max(lengths), len(vids)
 
-    def pad(src):
-        d = np.asarray(src[vids[0]]).shape[1]
+    def pad(kind):
+        d = src(kind, vids[0]).shape[1]
         out = np.zeros((T, B, d), np.float32)
         for b, v in enumerate(vids):
-            out[:lengths[b], b] = np.asarray(src[v], dtype=np.float32)
+            out[:lengths[b], b] = src(kind, v)
         return torch.from_numpy(out)
 
     q = np.zeros((T, B, 2), np.float32)
     u = np.zeros((B, T), np.float32)
     for b, v in enumerate(vids):
-        for t_, x in enumerate(spk[v]):
-            q[t_, b, 0 if x == "M" else 1] = 1
+        q[np.arange(lengths[b]), b, src("spk", v)] = 1
         u[b, :lengths[b]] = 1
-    return pad(text), pad(audio), pad(visual), torch.from_numpy(q), torch.from_numpy(u)
+    return pad("text"), pad("audio"), pad("visual"), torch.from_numpy(q), torch.from_numpy(u)
 
 
 def case_inputs(c, name):
@@ -93,7 +94,7 @@ def case_inputs(c, name):
         got = iemocap_batch([str(x) for x in c["vids"]])
         if got is None:
             import pytest
-            pytest.skip("reference feature pickle not staged under baseline/_ref/data (run __graft_entry__.build() where /root/reference exists)")
+            pytest.skip("IEMOCAP test dialogues not staged under baseline/_ref/data (run __graft_entry__.build() where /root/reference exists)")
         t, a, v, q, u = got
     elif "textf" in c:
         t, a, v, q, u = (torch.from_numpy(c[k]) for k in ("textf", "acouf", "visuf", "qmask", "umask"))

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in sigs:
         assert hasattr(L, name), name
     L.mmdfn_abi_version.restype = ctypes.c_int
-    assert L.mmdfn_abi_version() == 1
+    assert L.mmdfn_abi_version() == 2
 
 
 def test_header_prototypes_match_definitions():
