@@ -199,6 +199,12 @@ int mmdfn_focal_loss_fwd(int N, int C, const float* log_prob, const long long* t
 int mmdfn_focal_loss_bwd(int N, int C, const float* log_prob, const long long* target, const float* alpha,
                          float gamma, int size_average, const float* dloss, float* dlog_prob, void* stream);
 
+/* device-side evaluation metrics (replaces the per-batch argmax -> .cpu() -> sklearn of code/run_train_erc.py:202-203,
+ * 228-235): pred (N) int64 (nullable) = argmax over classes (first maximum), conf (C*C) uint64 (nullable) accumulates
+ * conf[target*C + pred] += 1 over as many batches as the caller likes. */
+int mmdfn_confusion_accumulate(int N, int C, const float* log_prob, const long long* target, long long* pred,
+                               unsigned long long* conf, void* stream);
+
 /* ---- k10/k11 (relation graph type): edges and masked edge attention ----------------------------
  * edge_perms + batch_graphify (code/model.py:532-550, 568-611) and MaskedEdgeAttention 'attn1' (:449-471).
  * Canonical edge order: dialogue, source j, target i ascending; edge_off (B+1) int64 = per-dialogue edge

@@ -317,3 +317,34 @@ extern "C" int mmdfn_log_softmax_bwd(int N, int C, const float* log_prob, const 
   MMDFN_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- device-side evaluation metrics (code/run_train_erc.py:202-203,228-235: argmax -> .cpu() per batch, then sklearn) ----
+// pred[n] = argmax_c log_prob[n, c] (first maximum, like torch.argmax); conf[target * C + pred] += 1.  The confusion
+// matrix of a whole epoch accumulates on the device; accuracy / weighted F1 follow from its C*C counts on the host.
+namespace mmdfn {
+__global__ void confusion_kernel(int N, int C, const float* __restrict__ lp, const long long* __restrict__ target,
+                                 long long* __restrict__ pred, unsigned long long* __restrict__ conf) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* row = lp + (i64)n * C;
+  int best = 0;
+  float bv = row[0];
+  for (int c = 1; c < C; c++) {
+    const float v = row[c];
+    if (v > bv) { bv = v; best = c; }
+  }
+  if (pred) pred[n] = best;
+  const long long t = target[n];
+  if (conf && t >= 0 && t < C) atomicAdd(conf + t * C + best, 1ULL);
+}
+}  // namespace mmdfn
+
+extern "C" int mmdfn_confusion_accumulate(int N, int C, const float* log_prob, const long long* target,
+                                          long long* pred, unsigned long long* conf, void* stream) {
+  if (!log_prob || !target) return MMDFN_ENULL;
+  if (C <= 0 || N < 0) return MMDFN_EINVAL;
+  if (N == 0) return 0;
+  mmdfn::confusion_kernel<<<mmdfn::ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(N, C, log_prob, target, pred, conf);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}

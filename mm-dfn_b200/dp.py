@@ -94,6 +94,7 @@ class FlatAdamTrainer:
         for p in self.params:
             p.grad = None                                         # autograd then stores each gradient without an add kernel
         log_prob = self.model(textf, qmask, umask, lengths, acouf, visuf)[0]
+        self.last_log_prob = log_prob.detach()                    # for the trainer loop's device-side metrics
         loss = self.loss_fn(log_prob, label)
         n_local = int(sum(lengths))
         if n_global is not None and n_global != n_local:

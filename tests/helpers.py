@@ -123,3 +123,24 @@ def grad_summary_of(named_grads):
 
 def spk_weights(c):
     return tuple(float(x) for x in str(c["spk_w"]).split("-"))
+
+
+def write_small_iemocap_pickle(path, n_train=24):
+    """A pickle in the author's IEMOCAP format (code/dataloader.py:12-14) holding the 31 staged IEMOCAP test dialogues:
+    the first `n_train` form the train split, the rest the test split.  Returns `path` (None if nothing is staged)."""
+    import pickle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    npz = os.path.join(root, "baseline", "_ref", "data", "iemocap_test_dialogues.npz")
+    if not os.path.exists(npz):
+        return None
+    z = np.load(npz, allow_pickle=False)
+    vids = [str(v) for v in z["vids"]]
+    ids = {v: list(range(len(z["label::" + v]))) for v in vids}
+    spk = {v: ["M" if s == 0 else "F" for s in z["spk::" + v]] for v in vids}
+    labels = {v: [int(x) for x in z["label::" + v]] for v in vids}
+    text = {v: [row for row in z["text::" + v]] for v in vids}
+    audio = {v: [row for row in z["audio::" + v]] for v in vids}
+    visual = {v: [row for row in z["visual::" + v]] for v in vids}
+    sent = {v: [""] * len(labels[v]) for v in vids}
+    pickle.dump((ids, spk, labels, text, audio, visual, sent, vids[:n_train], vids[n_train:]), open(path, "wb"))
+    return path
