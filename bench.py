@@ -48,12 +48,70 @@ METRIC = "utterances/sec (fwd+bwd) IEMOCAP-shape"
 UNIT = "utterances/s"
 
 
+IEMOCAP_TRAIN_LENGTHS = [30, 18, 49, 53, 51, 54, 69, 63, 79, 110, 26, 62, 51, 42, 78, 34, 35, 39, 43, 56, 47, 64, 52, 60, 28, 30, 35, 61, 37,
+                         62, 34, 66, 26, 66, 47, 53, 53, 74, 40, 43, 60, 61, 44, 46, 44, 47, 63, 74, 44, 58, 38, 26, 39, 18, 37, 40, 53, 94,
+                         47, 50, 87, 61, 37, 54, 69, 53, 54, 59, 43, 26, 50, 29, 51, 83, 35, 47, 32, 69, 32, 26, 26, 42, 60, 57, 50, 60, 52,
+                         47, 45, 27, 34, 72, 57, 53, 8, 31, 36, 33, 44, 56, 26, 41, 38, 46, 63, 42, 54, 51, 46, 44, 27, 44, 20, 58, 24, 59,
+                         77, 53, 45, 62]          # dialogue lengths of the IEMOCAP train split (120 dialogues, 5810 utterances)
+MELD_LENGTH_HIST = [(1, 76), (2, 64), (3, 61), (4, 52), (5, 76), (6, 69), (7, 78), (8, 74), (9, 55), (10, 65), (11, 68), (12, 62),
+                    (13, 42), (14, 46), (15, 46), (16, 53), (17, 34), (18, 28), (19, 31), (20, 23), (21, 21), (22, 15), (23, 8),
+                    (24, 5)]              # (length, count) over the MELD train split (1152 dialogues, 11098 utterances)
+
+
+def _lengths_uniform(i):
+    return [UTT] * DIALOGUES_PER_GPU
+
+
+def _lengths_ragged(i):
+    return [int(x) for x in np.random.RandomState(1 + i).randint(50, 111, size=DIALOGUES_PER_GPU)]       # L ~ U{50..110}, seed 1
+
+
+def _lengths_iemocap(i):
+    rs = np.random.RandomState(7)
+    order = rs.permutation(len(IEMOCAP_TRAIN_LENGTHS))
+    return [IEMOCAP_TRAIN_LENGTHS[j] for j in order[(i * DIALOGUES_PER_GPU) % 96:(i * DIALOGUES_PER_GPU) % 96 + DIALOGUES_PER_GPU]]
+
+
+def _lengths_meld(i):
+    pool = np.repeat([l for l, _ in MELD_LENGTH_HIST], [c for _, c in MELD_LENGTH_HIST])
+    return [int(x) for x in np.random.RandomState(11 + i).choice(pool, size=DIALOGUES_PER_GPU, replace=False)]
+
+
+# name -> (dialogues per GPU, max length, d_text, d_audio, d_visual, speakers, classes, layers, speaker weights, lengths(i), description)
+WORKLOADS = {
+    "c4": (32, 100, 100, 512, 1024, 2, 6, 2, "3-0-1", _lengths_uniform,
+           "BASELINE configs[1]/[3] (SURVEY C4 shape): synthetic IEMOCAP-shape, 32 dialogues x 100 utterances per GPU, 100/512/1024-d T/A/V"),
+    "c4-ragged": (32, 110, 100, 512, 1024, 2, 6, 2, "3-0-1", _lengths_ragged,
+                  "SURVEY 8d ragged variant of C4: 32 dialogues per GPU, L ~ U{50..110} (seed 1), 100/512/1024-d T/A/V"),
+    "c2": (32, 110, 100, 1582, 342, 2, 6, 2, "3-0-1", _lengths_iemocap,
+           "BASELINE configs[1] shape: IEMOCAP dims 100/1582/342 (T/A/V), bs=32 batches drawn from the real IEMOCAP train length list (8..110, mean 48.4)"),
+    "c3": (16, 24, 600, 300, 342, 9, 7, 4, "0.5-0.5-1.5", _lengths_meld,
+           "BASELINE configs[2] shape: MELD dims 600/300/342 (T/A/V), 9 speakers, 7 classes, 4 GCN layers, bs=16 batches drawn from the real MELD train length histogram (1..24, mean 9.6)"),
+    "c5": (64, 500, 100, 512, 1024, 8, 6, 6, "1-1-1", _lengths_uniform,
+           "BASELINE configs[4] shard: synthetic stress, 64 dialogues x 500 utterances per GPU, 8 speakers, 6 GCN layers, 100/512/1024-d T/A/V"),
+}
+WORKLOAD = "c4"
+LENGTHS_FN = _lengths_uniform
+WORKLOAD_DESC = WORKLOADS["c4"][10]
+
+
+def apply_workload(name, layers=None):
+    g = globals()
+    (g["DIALOGUES_PER_GPU"], g["UTT"], g["D_T"], g["D_A"], g["D_V"], g["SPEAKERS"], g["CLASSES"], g["LAYERS"], g["SPK_W"],
+     g["LENGTHS_FN"], g["WORKLOAD_DESC"]) = WORKLOADS[name]
+    g["WORKLOAD"] = name
+    if layers is not None:
+        g["LAYERS"] = max(0, layers)
+
+
 def workload_config(n_gpus):
     per_gpu_bytes = UTT * DIALOGUES_PER_GPU * (D_T + D_A + D_V + SPEAKERS) * 4
-    return {"workload": "BASELINE configs[1]/[3] (SURVEY C4 shape): synthetic IEMOCAP-shape, 32 dialogues x 100 "
-                        "utterances per GPU, 100/512/1024-d T/A/V, S=2, C=6, %d GCN layers + LSTM fusion gate, " % LAYERS +
+    return {"workload": WORKLOAD_DESC + ", S=%d, C=%d, %d GCN layers + LSTM fusion gate, " % (SPEAKERS, CLASSES, LAYERS) +
                         "crn-speaker encoders, dropout 0.4, FocalLoss(gamma=1), Adam(lr=1e-4, l2=1e-4)",
-            "dialogues_per_gpu": DIALOGUES_PER_GPU, "utterances_per_dialogue": UTT, "global_dialogues": DIALOGUES_PER_GPU * n_gpus,
+            "name": WORKLOAD,
+            "dialogues_per_gpu": DIALOGUES_PER_GPU, "utterances_per_dialogue": UTT if LENGTHS_FN is _lengths_uniform else
+            "ragged, mean %.1f" % float(np.mean([np.mean(LENGTHS_FN(i)) for i in range(N_BATCHES)])),
+            "global_dialogues": DIALOGUES_PER_GPU * n_gpus,
             "gcn_layers": LAYERS, "parallelism": f"dp{n_gpus} (dialogue shards, 1 NCCL all-reduce/step)",
             "l2_policy": f"inputs rotate over {N_BATCHES} distinct batches ({N_BATCHES * per_gpu_bytes / 1e6:.0f} MB > 126 MB L2)"}
 
@@ -83,10 +141,14 @@ def synthetic_batch(lengths, seed):
 
 
 def make_batches(n, seed0):
-    return [synthetic_batch([UTT] * DIALOGUES_PER_GPU, seed0 + i) for i in range(n)]
+    return [synthetic_batch(LENGTHS_FN(i), seed0 + i) for i in range(n)]
 
 
 def class_weights():
+    """inverse class frequencies of code/run_train_erc.py:398-414"""
+    if CLASSES == 7:
+        return torch.tensor([1.0 / 0.466750766, 1.0 / 0.122094071, 1.0 / 0.027752748, 1.0 / 0.071544422, 1.0 / 0.171742656,
+                             1.0 / 0.026401153, 1.0 / 0.113714183])
     return torch.tensor([1 / 0.086747, 1 / 0.144406, 1 / 0.227883, 1 / 0.160585, 1 / 0.127711, 1 / 0.252668])
 
 
@@ -101,10 +163,10 @@ def cpu_reference_steps(steps, warmup, n_dialogues=CPU_SAMPLE_DIALOGUES, max_sec
     import ref_shim
     from helpers import model_shapes
     torch.set_num_threads(os.cpu_count() or 1)
-    lengths = [UTT] * n_dialogues
+    lengths = LENGTHS_FN(0)[:n_dialogues]
     t, a, v, q, u, lab = O.synthetic_batch(lengths, D_T, D_A, D_V, SPEAKERS, CLASSES, seed=100)
     cw = class_weights()
-    T, B, N = UTT, n_dialogues, sum(lengths)
+    T, B, N = max(lengths), len(lengths), sum(lengths)
     code_dir = ref_shim.ref_code_dir(ROOT)
     if code_dir is not None:
         kind = "reference"
@@ -112,7 +174,8 @@ def cpu_reference_steps(steps, warmup, n_dialogues=CPU_SAMPLE_DIALOGUES, max_sec
         torch.manual_seed(2021)
         import contextlib
         with contextlib.redirect_stdout(sys.stderr):
-            model = ref_shim.make_reference_model(model_mod, D_T, D_A, D_V, SPEAKERS, CLASSES, LAYERS, "IEMOCAP", SPK_W, DROPOUT)
+            model = ref_shim.make_reference_model(model_mod, D_T, D_A, D_V, SPEAKERS, CLASSES, LAYERS,
+                                                  "MELD" if CLASSES == 7 else "IEMOCAP", SPK_W, DROPOUT)
         model.train()
         loss_f = loss_mod.FocalLoss(gamma=GAMMA, alpha=cw)
         opt = torch.optim.Adam(model.parameters(), lr=LR, weight_decay=L2)
@@ -166,7 +229,7 @@ def cpu_reference_steps(steps, warmup, n_dialogues=CPU_SAMPLE_DIALOGUES, max_sec
     sec = float(np.mean(times))
     return {"utt_per_s": N / sec, "sec_per_step": sec, "steps_timed": len(times), "warmup_done": warm_done,
             "cores": torch.get_num_threads(), "kind": kind,
-            "sample": f"{n_dialogues} of the workload's {DIALOGUES_PER_GPU} dialogues x {UTT} utterances per step "
+            "sample": f"{len(lengths)} of the workload's {DIALOGUES_PER_GPU} dialogues (lengths {min(lengths)}..{max(lengths)}) per step "
                       f"({N} utterances; the reference's dense (3N)^2 adjacency makes its throughput fall with batch size), "
                       f"{'unmodified reference code/model.py' if kind == 'reference' else 'oracle port'}, "
                       f"train mode, fwd+bwd+Adam, dropout {DROPOUT}, mean of {len(times)} steps after {warm_done} warm-up"}
@@ -189,13 +252,14 @@ def run_reference_arm(args, out):
     print(json.dumps(reference_line(args, r)), file=out, flush=True)
 
 
-def cpu_baseline_subprocess(layers):
+def cpu_baseline_subprocess(layers, dialogues=CPU_SAMPLE_DIALOGUES):
     """cpu_baseline of the product line: the reference arm run as its own process (the shim patches torch.Tensor
     globally, which must not leak into the process that drives the GPU), bounded to ~60 s."""
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
     env["CUDA_VISIBLE_DEVICES"] = ""
     r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", "1", "--steps", "8", "--warmup", "2",
-                        "--layers", str(layers), "--ref-seconds", "60"], capture_output=True, text=True, timeout=400, env=env)
+                        "--layers", str(layers), "--ref-seconds", "60", "--workload", WORKLOAD, "--ref-dialogues", str(dialogues)],
+                       capture_output=True, text=True, timeout=400, env=env)
     line = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")][-1]
     return json.loads(line)["cpu_baseline"]
 
@@ -257,7 +321,7 @@ def roofline_graph_conv(dev, n_dialogues=DIALOGUES_PER_GPU):
     flag bytes the kernel also moves are NOT counted."""
     from mmdfn_b200 import ops
     from mmdfn_b200._lib import call, ptr, ptr_table, query, stream
-    lengths = [UTT] * n_dialogues
+    lengths = [UTT] * n_dialogues if (LENGTHS_FN is _lengths_uniform or n_dialogues != DIALOGUES_PER_GPU) else LENGTHS_FN(0)
     geom = ops.DialogGeom(lengths, dev)
     N, G = geom.N, 100
     n3 = 3 * N
@@ -337,8 +401,9 @@ def roofline_graph_conv(dev, n_dialogues=DIALOGUES_PER_GPU):
             "algorithmic_bytes_per_launch": alg_bytes, "bytes_moved_per_launch_incl_q_mask_flags": moved_bytes,
             "us_per_launch": us, "peak_source": how,
             "same_bytes_copy_kernel": {"us_per_launch": us_copy, "frac": alg_bytes / (us_copy * 1e-6) / 1e9 / peak},
-            "note": "launch covers one whole GCN layer (SURVEY 8d k6 bytes) of the %dx100 shard; %d back-to-back launches (%s), "
+            "note": "launch covers one whole GCN layer (SURVEY 8d k6 bytes) of a %d-dialogue shard of this workload; %d back-to-back launches (%s), "
                     "operands rotated over %d copies (> L2)" % (n_dialogues, reps, mode, copies)}
+
 
 
 def _claim_stdout():
@@ -363,10 +428,15 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured whole-step CUDA graph")
     ap.add_argument("--ref-dialogues", type=int, default=CPU_SAMPLE_DIALOGUES, help="reference arm: dialogues per CPU step")
     ap.add_argument("--ref-seconds", type=float, default=170.0, help="reference arm: wall-clock bound of the whole run")
-    ap.add_argument("--layers", type=int, default=LAYERS, help="GCN layers (default 2 = BASELINE configs[1]; the authors' "
+    ap.add_argument("--layers", type=int, default=None, help="GCN layers (default: the workload's; c4: 2 = BASELINE configs[1]; the authors' "
                     "IEMOCAP script uses 16) -- any other value is an extra data point, not the headline workload")
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS), help="c4 = the default / headline workload; the others are "
+                    "extra data points (SURVEY 8d): c4-ragged, c2 (IEMOCAP dims + real length list), c3 (MELD shape), c5 (500-utterance stress shard)")
+    ap.add_argument("--ragged", action="store_true", help="shorthand for --workload c4-ragged")
     args = ap.parse_args()
-    globals()["LAYERS"] = max(0, args.layers)          # read by workload_config / the model constructor / the CPU port
+    if args.ragged:
+        args.workload = "c4-ragged"
+    apply_workload(args.workload, args.layers)
     if args.impl == "reference":
         return run_reference_arm(args, real_stdout)
 
@@ -405,23 +475,26 @@ def main():
     host = make_batches(N_BATCHES, seed0=1000 * (rank + 1))              # each rank owns different dialogues
     pinned = [tuple(x.pin_memory() for x in b) for b in host]
     resident = [tuple(x.to(dev) for x in b) for b in host]
-    lengths = [UTT] * DIALOGUES_PER_GPU
-    n_local = sum(lengths)
-    n_global = n_local * world
-    h2d_bytes = sum(x.numel() * x.element_size() for x in host[0])
+    batch_lengths = [LENGTHS_FN(i) for i in range(N_BATCHES)]            # the same geometry on every rank, different data
+    n_utt = [sum(x) for x in batch_lengths]
+    h2d_bytes = int(np.mean([sum(x.numel() * x.element_size() for x in b) for b in host]))
+
+    def utterances(steps):
+        return sum(n_utt[i % N_BATCHES] for i in range(steps)) * world
 
     res_events = []
     use_graph = [False]
 
-    def run_step(t, a, v, q, u, lab):
+    def run_step(i, t, a, v, q, u, lab):
         """the public API call of one training step: FlatAdamTrainer.replay (captured CUDA graph) or .step (eager)"""
+        lengths = batch_lengths[i % N_BATCHES]
         if use_graph[0]:
-            return trainer.replay(t, q, u, a, v, lab)
-        return trainer.step(t, q, u, lengths, a, v, lab, n_global)
+            return trainer.replay(t, q, u, a, v, lab, lengths)
+        return trainer.step(t, q, u, lengths, a, v, lab, n_utt[i % N_BATCHES] * world)
 
     def step_resident(i):
         t, a, v, q, u, lab = resident[i % N_BATCHES]
-        out = run_step(t, a, v, q, u, lab)
+        out = run_step(i, t, a, v, q, u, lab)
         # keep the host at most two steps ahead of the device: unbounded run-ahead makes the caching allocator grow
         # (blocks used on the side stream cannot be recycled before their events complete) and a cudaMalloc in the
         # timed region stalls the queue -- measured as 3.3 -> 3.7 .. 6.7 ms/step run-to-run noise
@@ -454,7 +527,7 @@ def main():
         torch.cuda.current_stream(dev).wait_event(ev)
         for x in (t, a, v, q, u, lab):
             x.record_stream(torch.cuda.current_stream(dev))
-        loss = run_step(t, a, v, q, u, lab)
+        loss = run_step(i, t, a, v, q, u, lab)
         # D2H read of the step's result, every step: an asynchronous 4-byte copy into pinned memory behind the step's
         # kernels; the host consumes it one step later (and the last one before the timed region closes), so the read
         # does not drain the launch queue -- what a training loop that logs the loss does
@@ -509,12 +582,16 @@ def main():
         try:
             torch.cuda.synchronize()
             res_events.clear()
-            l0 = query("mmdfn_launch_count")
-            t, a, v, q, u, lab = resident[0]
-            trainer.capture(t, q, u, lengths, a, v, lab, n_global, warmup=0)
-            launches_per_step = query("mmdfn_launch_count") - l0
+            # one captured graph per distinct batch geometry (uniform workloads: one; ragged ones: one per rotating batch)
+            for i in range(N_BATCHES):
+                if trainer.has_graph(batch_lengths[i]):
+                    continue
+                l0 = query("mmdfn_launch_count")
+                t, a, v, q, u, lab = resident[i]
+                trainer.capture(t, q, u, batch_lengths[i], a, v, lab, n_utt[i] * world, warmup=0)
+                launches_per_step = query("mmdfn_launch_count") - l0
             use_graph[0] = True
-            graph_note = "whole step (fwd+bwd+all-reduce+Adam) replayed as one captured CUDA graph"
+            graph_note = "whole step (fwd+bwd+all-reduce+Adam) replayed as one captured CUDA graph (%d geometries captured)" % len(trainer._graphs)
         except Exception as e:  # pragma: no cover
             use_graph[0] = False
             graph_note = "eager launches (graph capture failed: %r)" % (e,)
@@ -539,11 +616,12 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
-        value = n_global * K / sec
+        n_total = utterances(K)
+        value = n_total / sec
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": sec / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(world),
-                "e2e": {"value": n_global * K / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "e2e": {"value": n_total / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": sec_e2e / K * 1e3,
                         "note": "inputs pinned-host -> device every step on a copy stream one batch ahead; the loss is copied D2H "
                                 "every step (async, pinned) and consumed by the host one step later, all %d inside the timed region" % K},
@@ -551,13 +629,14 @@ def main():
         line["config"]["launch_mode"] = graph_note
         try:
             line["roofline"] = roofline_graph_conv(dev)
-            big = roofline_graph_conv(dev, 256)          # BASELINE config 4 on one GPU (256 x 100 utterances): steady-state view
-            line["roofline"]["at_256_dialogues"] = {k: big[k] for k in ("achieved", "frac", "us_per_launch", "algorithmic_bytes_per_launch", "same_bytes_copy_kernel")}
+            if WORKLOAD == "c4":
+                big = roofline_graph_conv(dev, 256)      # BASELINE config 4 on one GPU (256 x 100 utterances): steady-state view
+                line["roofline"]["at_256_dialogues"] = {k: big[k] for k in ("achieved", "frac", "us_per_launch", "algorithmic_bytes_per_launch", "same_bytes_copy_kernel")}
         except Exception as e:  # pragma: no cover
             line["roofline"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline_subprocess(LAYERS)
+                line["cpu_baseline"] = cpu_baseline_subprocess(LAYERS, {"c5": 2, "c3": 16}.get(WORKLOAD, CPU_SAMPLE_DIALOGUES))
             except Exception as e:  # pragma: no cover
                 line["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(line), file=real_stdout, flush=True)

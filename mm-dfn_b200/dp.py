@@ -136,7 +136,9 @@ class FlatAdamTrainer:
         (dropout counter, Adam step index / bias corrections) are read from a device-resident state, so replays draw fresh
         masks and apply the right corrections.  The eager `step` keeps working for other shapes (it shares the state)."""
         from . import ops
+        from .modules import _geom_of
         dev = self.flat_p.device
+        _geom_of(lengths, dev)                  # host -> device copies of the geometry happen here, not inside the capture
         self._static = tuple(torch.empty_like(x) for x in (textf, qmask, umask, acouf, visuf, label))
         for dst, src in zip(self._static, (textf, qmask, umask, acouf, visuf, label)):
             dst.copy_(src)
