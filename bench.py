@@ -43,7 +43,7 @@ N_BATCHES = 8                      # distinct input batches rotated so that step
 CPU_SAMPLE_DIALOGUES = 8
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE gcn_layer_kernel<fwd> launch inside a training step of the default
 # workload, read from the committed `ncu --set full` capture (profiles/, see profiles/README.md); None = not captured yet
-NCU_TRAFFIC_BYTES = None
+NCU_TRAFFIC_BYTES = 17593088          # profiles/r02_ncu_gcn_layer_and_gemm2.csv: 17.59 MB read + 0 written (outputs stay in L2)
 METRIC = "utterances/sec (fwd+bwd) IEMOCAP-shape"
 UNIT = "utterances/s"
 

@@ -57,6 +57,10 @@ int mmdfn_gemm_tc_set_debug(long long* device_buf);
 int mmdfn_gemm_tc_set_variant(int v);
 /* debug aid: reads back the shared-memory word the tensor core uses for each operand element (see umma_probe.cu) */
 int mmdfn_umma_probe(float* out, int N, int lbo, int sbo, int mn_major, int probe_a, void* stream);
+/* debug aid: one product with the A operand in tensor memory; out (128 x 16) must read back 16 m + n */
+int mmdfn_umma_probe_ta(float* out, int a_col, void* stream);
+/* zero-fill `bytes` bytes at p with cudaMemsetAsync on `stream` (gradient buffers: a memset node instead of a fill kernel) */
+int mmdfn_memset_zero(void* p, long long bytes, void* stream);
 /* out[n] = beta*out[n] + sum_m A[m*lda+n]   (bias gradients) */
 int mmdfn_colsum(int M, int N, const float* A, long long lda, float beta, float* out, void* stream);
 

@@ -267,8 +267,11 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gcn_layer_kernel(GcnLayerArgs p
         if (c >= NS) umma::mbar_wait(&bar_free[s], (uint32_t)(((c / NS) - 1) & 1));
         if (dbg_on && c < 60) p.dbg[128 + c] = clock64();                            // converter: stage free
         uint8_t* st = stages + s * STAGE;
+        const bool fine = dbg_on && c == 3;
+        if (fine) p.dbg[240] = clock64();
 #pragma unroll
         for (int i = 0; i < NPA; i++) gl_split_store(va[u][i], st + o_a[i], st + A_PART + o_a[i]);
+        if (fine) p.dbg[241] = clock64();
 #pragma unroll
         for (int i = 0; i < NPB; i++) {
           if (o_b[i] >= 0) {
@@ -285,7 +288,13 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gcn_layer_kernel(GcnLayerArgs p
             gl_split_store(v, st + 2 * A_PART + o_b[i], st + 2 * A_PART + B_PART + o_b[i]);
           }
         }
-        umma::warp_arrive_full(&bar_full[s]);
+        if (fine) p.dbg[242] = clock64();
+        umma::fence_proxy_async_smem();
+        if (fine) p.dbg[243] = clock64();
+        __syncwarp();
+        if (fine) p.dbg[244] = clock64();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(&bar_full[s])) : "memory");
+        if (fine) p.dbg[245] = clock64();
         // prefetch AFTER the hand-off: fence.proxy.async waits for the thread's outstanding global loads (measured:
         // ~1 k cycles per chunk when the next pieces were requested before it)
         if (c + ADEPTH < nchA) load_a(c + ADEPTH, va[u]);
@@ -400,14 +409,22 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gcn_layer_kernel(GcnLayerArgs p
     if (g >= NS) umma::mbar_wait(&bar_free[s], (uint32_t)(((g / NS) - 1) & 1));
     if (dbg_on && g < 60) p.dbg[128 + g] = clock64();
     uint8_t* st = stages + s * STAGE;
+    const bool fine = dbg_on && c == 3;
+    if (fine) p.dbg[248] = clock64();
 #pragma unroll
     for (int i = 0; i < NPA; i++) gl_split_store(ta[i], st + o_a[i], st + A_PART + o_a[i]);
+    if (fine) p.dbg[249] = clock64();
 #pragma unroll
     for (int u = 0; u < WP; u++) {
       const int i = tid + u * GL_CONV;
       if (i < 2 * B_PART / 16) *reinterpret_cast<float4*>(st + 2 * A_PART + i * 16) = wb[u];
     }
-    umma::warp_arrive_full(&bar_full[s]);
+    if (fine) p.dbg[250] = clock64();
+    umma::fence_proxy_async_smem();
+    if (fine) p.dbg[251] = clock64();
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(&bar_full[s])) : "memory");
+    if (fine) p.dbg[252] = clock64();
     if (c + 1 < WCHUNKS) load_w(c + 1);                      // after the fence (see phase A)
   }
   GL_STAMP();                                                // [5] phase B converted

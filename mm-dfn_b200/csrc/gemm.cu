@@ -168,6 +168,14 @@ extern "C" int mmdfn_gemm(int transA, int transB, int M, int N, int K, float alp
                      (cudaStream_t)stream);
 }
 
+/* zero-fill through cudaMemsetAsync (a memset node: no fill kernel on the stream) */
+extern "C" int mmdfn_memset_zero(void* p, long long bytes, void* stream) {
+  if (bytes < 0) return MMDFN_EINVAL;
+  if (bytes == 0) return 0;
+  if (!p) return MMDFN_ENULL;
+  return mmdfn::fill_zero(p, (size_t)bytes, (cudaStream_t)stream);
+}
+
 extern "C" int mmdfn_colsum(int M, int N, const float* A, long long lda, float beta, float* out, void* stream) {
   if (!A || !out) return MMDFN_ENULL;
   return mmdfn::colsum(M, N, A, lda, beta, out, (cudaStream_t)stream);

@@ -11,6 +11,10 @@ int gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64
 // same contract on tcgen05 (3xTF32)
 int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64 lda, const float* B, i64 ldb,
               float beta, float* C, i64 ldc, const float* bias, int act, cudaStream_t st);
+// second-generation tcgen05 kernel for 16-byte-aligned problems (umma_gemm2.cu); `splits` as chosen by umma_gemm
+bool umma_gemm2_eligible(bool ta, bool tb, int M, int N, int K, const float* A, i64 lda, const float* B, i64 ldb);
+int umma_gemm2(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64 lda, const float* B, i64 ldb,
+               float beta, float* C, i64 ldc, const float* bias, int act, int splits, cudaStream_t st);
 // out[n] = beta*out[n] + sum_m A[m*lda + n]
 int colsum(int M, int N, const float* A, i64 lda, float beta, float* out, cudaStream_t st);
 int fill_zero(void* p, size_t bytes, cudaStream_t st);

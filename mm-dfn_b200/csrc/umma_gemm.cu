@@ -502,6 +502,12 @@ int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A
     ug_scale2d_kernel<<<(unsigned)ceil_div64((i64)M * N, 256), 256, 0, st>>>(C, ldc, M, N, beta);
     MMDFN_LAUNCH_CHECK();
   }
+  // aligned NT problems (x W^T: projections, GRU / LSTM gate products) go to the second-generation kernel (register
+  // operand path, umma_gemm2.cu): measured 1.2-1.27x on the path's shapes (profiles/r02_umma_gemm_gen2.log).  Its NN / TN
+  // forms (TMA raw ring + transposed reads) measured 0.7-1.1x of this kernel and stay opt-in: variant 2 forces the second
+  // generation for every eligible form, variant 1 keeps everything on the first generation (A/B timing, cross-checks).
+  if (bn == 112 && g_ug_variant != 1 && ((!ta && tb) || g_ug_variant == 2) && umma_gemm2_eligible(ta, tb, M, N, K, A, lda, B, ldb))
+    return umma_gemm2(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act, p.splits, st);
   if (!ta && tb) return dispatch_bn<0>(p, bn, st);
   if (!ta && !tb) return dispatch_bn<1>(p, bn, st);
   return dispatch_bn<2>(p, bn, st);

@@ -46,7 +46,71 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(float* out, int N, i
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, 256);
 }
+
+// Second probe: the A operand read from TENSOR MEMORY (tcgen05.mma [d], [a_tmem], b_desc).  Thread m writes
+// A(m, k) = 16 m + k, k = 0..15, into 16 consecutive TMEM columns of its lane with tcgen05.st.32x32b; B = 16 x 16
+// identity (K-major, known-good layout); two K = 8 MMAs, the second with the A address advanced by 8 columns.
+// out[m][n] must read back 16 m + n.
+__global__ void __launch_bounds__(128, 1) umma_probe_ta_kernel(float* out, int a_col) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* ident = reinterpret_cast<float*>(smem);                 // identity operand, K-major (SBO 528, LBO 128)
+  for (int i = tid; i < 4096; i += 128) ident[i] = 0.f;
+  __syncthreads();
+  if (tid < 16) ident[((tid >> 3) * 528 + (tid >> 2) * 128 + (tid & 7) * 16 + (tid & 3) * 4) / 4] = 1.0f;   // (n = tid, k = tid)
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 256);
+  if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_barrier_init(); }
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  {
+    uint32_t r[16];
+    for (int k = 0; k < 16; k++) r[k] = __float_as_uint((float)(16 * tid + k));
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)a_col;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  if (tid == 0) {
+    const uint32_t base = umma::smem_u32(ident);
+    const uint32_t idesc = umma::idesc_tf32(128, 16);
+    for (int j = 0; j < 2; j++) {
+      const uint64_t bdesc = umma::smem_desc(base + j * 256, 128, 528);
+      umma::mma_tf32_ta(tmem, tmem + (uint32_t)a_col + 8 * j, bdesc, idesc, j > 0 ? 1u : 0u);
+    }
+    umma::mma_commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::tc_fence_after_sync();
+  {
+    float v[16];
+    umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+    for (int q = 0; q < 16; q++) out[tid * 16 + q] = v[q];
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
+}
 }  // namespace mmdfn
+
+extern "C" int mmdfn_umma_probe_ta(float* out, int a_col, void* stream) {
+  using namespace mmdfn;
+  if (!out) return MMDFN_ENULL;
+  if (a_col < 16 || a_col > 240) return MMDFN_EINVAL;
+  umma_probe_ta_kernel<<<1, 128, 16384, (cudaStream_t)stream>>>(out, a_col);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int mmdfn_umma_probe(float* out, int N, int lbo, int sbo, int mn_major, int probe_a, void* stream) {
   using namespace mmdfn;

@@ -51,33 +51,98 @@ def shard_dialogues(n_dialogues, rank, world):
     return lo, lo + per + (1 if rank < rem else 0)
 
 
-class FlatAdamTrainer:
-    """Flat parameter / gradient buckets + one all-reduce + one fused Adam launch per step."""
+def gradient_groups(model):
+    """[(sink key, [parameters in the order of the backward function's internal gradient buffer])] for the GDF model,
+    early-final groups first: the head and graph-stack gradients are complete ~1 ms before the encoder gradients, so
+    they form the first all-reduce bucket.  None for configurations whose functions do not write into a sink."""
+    if getattr(model, "graph_type", None) != "GDF":
+        return None
+    from . import ops
+    net = model.graph_model.graph_net
+    gcn = [net.fcs[0].weight, net.fcs[0].bias]
+    if net.reason_flag and len(net.convs) > 0:
+        gcn += [net.rnn.weight_ih_l0, net.rnn.weight_hh_l0, net.rnn.bias_ih_l0, net.rnn.bias_hh_l0]
+    gcn += [c.weight for c in net.convs]
+    groups = [("head", [model.smax_fc.weight, model.smax_fc.bias]), ("gcn", gcn)]
+    if model.use_crn_speaker:
+        groups.append(("gru_p", [getattr(model.rnn_parties, ops.GRU_KEYS[i]) for i in ops._GRU_GRAD_ORDER]))
+    groups.append(("gru_l", [getattr(model.lstm_l, ops.GRU_KEYS[i]) for i in ops._GRU_GRAD_ORDER]))
+    groups.append(("proj", [model.linear_a.weight, model.linear_a.bias, model.linear_v.weight, model.linear_v.bias,
+                            model.linear_l.weight, model.linear_l.bias]))
+    return groups
 
-    def __init__(self, model, loss_fn, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, process_group=None):
+
+EARLY_KEYS = ("head", "gcn")          # first all-reduce bucket (final when the graph stack's backward returns)
+
+
+class FlatAdamTrainer:
+    """Flat parameter / gradient buckets + all-reduce + one fused Adam launch per step.
+
+    GDF models run in *direct* mode: the backward functions write every weight gradient straight into this trainer's
+    bucket (ops.GradSink; the bucket is zeroed by one memset per step, nothing is gathered afterwards), and the
+    all-reduce is split in two: the head + graph-stack segment is reduced on NCCL's stream as soon as the stack's
+    backward has been enqueued, i.e. while adjacency / party-pack / GRU / projection backward kernels still run; the
+    encoder segment follows at the end.  Other configurations (relation graph type) use the gather path."""
+
+    def __init__(self, model, loss_fn, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, process_group=None,
+                 direct_grads=None):
         self.model, self.loss_fn = model, loss_fn
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         named = used_parameters(model)
-        self.names = [n for n, _ in named]
-        params = [p for _, p in named]
+        groups = gradient_groups(model) if direct_grads is not False else None
+        if groups is not None:
+            # bucket order = group order; must cover exactly the used parameters
+            order = [p for _, ps in groups for p in ps]
+            if sorted(id(p) for p in order) != sorted(id(p) for _, p in named):
+                groups = None
+        if direct_grads and groups is None:
+            raise ValueError("direct_grads needs a GDF model")
+        name_of = {id(p): n for n, p in named}
+        params = [p for _, ps in groups for p in ps] if groups is not None else [p for _, p in named]
+        self.names = [name_of[id(p)] for p in params]
         dev = params[0].device
-        total = sum(p.numel() for p in params)
-        self.flat_p = torch.empty(total, device=dev, dtype=torch.float32)
+        # bucket layout: parameters back to back; in direct mode every gradient group starts on a 256-byte boundary (the
+        # split-K weight-gradient kernels reduce into the bucket with 128-bit atomics, which need 16-byte aligned rows --
+        # the head's C*900 + C floats would otherwise shift every later group off alignment).  Pad floats stay zero in
+        # the parameter, gradient and moment buckets, so Adam leaves them at zero.
+        ALIGN = 64
+        offs, seg_range, off = [], {}, 0
+        if groups is not None:
+            for key, ps in groups:
+                off = (off + ALIGN - 1) // ALIGN * ALIGN
+                start = off
+                for q in ps:
+                    offs.append(off)
+                    off += q.numel()
+                seg_range[key] = (start, off)
+        else:
+            for q in params:
+                offs.append(off)
+                off += q.numel()
+        total = off
+        self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
-        off = 0
         self.params, self.grad_views = params, []
-        for p in params:
-            n = p.numel()
-            self.flat_p[off:off + n].copy_(p.data.reshape(-1))
-            p.data = self.flat_p[off:off + n].view_as(p)          # parameters become views of the bucket
-            self.grad_views.append(self.flat_g[off:off + n].view_as(p))
-            p.grad = None
-            off += n
+        for q, off in zip(params, offs):
+            n = q.numel()
+            self.flat_p[off:off + n].copy_(q.data.reshape(-1))
+            q.data = self.flat_p[off:off + n].view_as(q)          # parameters become views of the bucket
+            self.grad_views.append(self.flat_g[off:off + n].view_as(q))
+            q.grad = None
         self.total = total
+        self.sink = None
+        if groups is not None:
+            from . import ops
+            self.sink = ops.GradSink()
+            for key, (a, b) in seg_range.items():
+                self.sink.seg[key] = self.flat_g[a:b]
+            self.early = max(seg_range[k][1] for k in EARLY_KEYS)                 # bucket A = flat_g[:early]
+            self.sink.on_ready = self._group_ready
+        self._early_work = None
         self.step_count = 0
         self._state = None            # device-resident step state (graph mode, see capture())
         self._graph = None            # most recently captured step
@@ -88,30 +153,50 @@ class FlatAdamTrainer:
         if self.world > 1:                                        # replicas start identical
             dist.broadcast(self.flat_p, src=0, group=self.pg)
 
+    def _group_ready(self, key):
+        """called from the backward when a gradient group is final: after the graph stack (the head came earlier), start
+        reducing bucket A on NCCL's stream -- it overlaps the rest of the backward"""
+        if key == "gcn" and self.world > 1 and self._early_work is None:
+            self._early_work = dist.all_reduce(self.flat_g[:self.early], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+
     def step(self, textf, qmask, umask, lengths, acouf, visuf, label, n_global=None):
         """One fwd + bwd + (all-reduce) + Adam step on this rank's shard.  Returns the local loss tensor
         (already scaled by N_rank/N_global; the sum over ranks is the global mean loss)."""
         for p in self.params:
             p.grad = None                                         # autograd then stores each gradient without an add kernel
-        log_prob = self.model(textf, qmask, umask, lengths, acouf, visuf)[0]
-        self.last_log_prob = log_prob.detach()                    # for the trainer loop's device-side metrics
-        loss = self.loss_fn(log_prob, label)
-        n_local = int(sum(lengths))
-        if n_global is not None and n_global != n_local:
-            loss = loss * (float(n_local) / float(n_global))
-        loss.backward()
+        from . import ops
+        if self.sink is not None:
+            call("mmdfn_memset_zero", self.flat_g.data_ptr(), self.total * 4, stream())     # the step's ONE gradient zero-fill
+            self._early_work = None
+        with ops.use_sink(self.sink):
+            log_prob = self.model(textf, qmask, umask, lengths, acouf, visuf)[0]
+            self.last_log_prob = log_prob.detach()                # for the trainer loop's device-side metrics
+            loss = self.loss_fn(log_prob, label)
+            n_local = int(sum(lengths))
+            if n_global is not None and n_global != n_local:
+                loss = loss * (float(n_local) / float(n_global))
+            loss.backward()
         if not self._checked:
             # once per trainer: the bucket must hold exactly the parameters that receive a gradient -- a parameter
             # outside it would silently stay at its initial value, one inside it without a gradient would be decayed
             self._checked = True
             stray = [n for n, p in self._outside if p.grad is not None]
-            missing = [n for n, p in zip(self.names, self.params) if p.grad is None]
-            if stray or missing:
-                raise RuntimeError(f"FlatAdamTrainer bucket mismatch: gradients outside the bucket {stray}, "
-                                   f"bucket parameters without a gradient {missing}")
-        torch._foreach_copy_(self.grad_views, [p.grad for p in self.params])   # one multi-tensor gather into the bucket
-        if self.world > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+            missing = [] if self.sink is not None else [n for n, p in zip(self.names, self.params) if p.grad is None]
+            leaked = [n for n, p in zip(self.names, self.params) if p.grad is not None] if self.sink is not None else []
+            if stray or missing or leaked:
+                raise RuntimeError(f"FlatAdamTrainer bucket mismatch: gradients outside the bucket {stray}, bucket parameters "
+                                   f"without a gradient {missing}, direct-mode parameters that still got an autograd gradient {leaked}")
+        if self.sink is None:
+            torch._foreach_copy_(self.grad_views, [p.grad for p in self.params])   # one multi-tensor gather into the bucket
+            if self.world > 1:
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+        elif self.world > 1:
+            if self._early_work is not None:
+                dist.all_reduce(self.flat_g[self.early:], op=dist.ReduceOp.SUM, group=self.pg)     # bucket B: encoder gradients
+                self._early_work.wait()                           # current stream waits for bucket A
+                self._early_work = None
+            else:
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
         if self._state is not None:
             # graph mode: the step index and Adam's bias corrections live on the device (captured launches cannot
             # take per-step arguments)

@@ -136,10 +136,11 @@ class GCNII_lyc(nn.Module):
             mx, mh = ops.make_mask((n3, 200), p, dev), ops.make_mask((n3, 100), p, dev)
             ml = ops.make_mask((K, n3, 100), p, dev) if K > 0 else None
             scale = 1.0 / (1.0 - p)
-        return ops.GCNStackFn.apply(x, adj.blk, adj.diag, geom, K, self.reason_flag, self.lamda, self.alpha, mx, mh, ml,
-                                    scale, self.fcs[0].weight, self.fcs[0].bias, self.rnn.weight_ih_l0,
-                                    self.rnn.weight_hh_l0, self.rnn.bias_ih_l0, self.rnn.bias_hh_l0,
-                                    *[c.weight for c in self.convs])
+        with ops.sink_key("gcn"):
+            return ops.GCNStackFn.apply(x, adj.blk, adj.diag, geom, K, self.reason_flag, self.lamda, self.alpha, mx, mh, ml,
+                                        scale, self.fcs[0].weight, self.fcs[0].bias, self.rnn.weight_ih_l0,
+                                        self.rnn.weight_hh_l0, self.rnn.bias_ih_l0, self.rnn.bias_hh_l0,
+                                        *[c.weight for c in self.convs])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -418,8 +419,9 @@ class DialogueGNNModel(nn.Module):
             pooled = ops.make_masks(shapes, p, dev)
         m_l = pooled[0] if train_drop else mk.get("gru_l")
         # k1: the three projections into one stacked table (a, v, l)
-        Utab = ops.Proj3Fn.apply(U_a, U_v, U, self.linear_a.weight, self.linear_a.bias, self.linear_v.weight,
-                                 self.linear_v.bias, self.linear_l.weight, self.linear_l.bias)
+        with ops.sink_key("proj"):
+            Utab = ops.Proj3Fn.apply(U_a, U_v, U, self.linear_a.weight, self.linear_a.bias, self.linear_v.weight,
+                                     self.linear_v.bias, self.linear_l.weight, self.linear_l.bias)
         # k2: text BiGRU over the padded sequence.  It is independent of the speaker-party encoder below and both are
         # few-CTA, latency-bound recurrences, so it runs on a side stream (autograd replays the same stream in backward).
         main = torch.cuda.current_stream(dev)
@@ -427,17 +429,18 @@ class DialogueGNNModel(nn.Module):
         tile_l, tile_p = ops.plan_gru_tiles(T, B, 3 * B * S) if side is not None else (0, 0)
         if side is not None:
             side.wait_stream(main)
-            with torch.cuda.stream(side), ops.gru_tile(tile_l):
+            with torch.cuda.stream(side), ops.gru_tile(tile_l), ops.sink_key("gru_l"):
                 E_l = ops.BiGRU2Fn.apply(Utab[2].reshape(T * B, 200), None, T, B, m_l, scale, *self._gru_weights(self.lstm_l))
         else:
-            E_l = ops.BiGRU2Fn.apply(Utab[2].reshape(T * B, 200), None, T, B, m_l, scale, *self._gru_weights(self.lstm_l))
+            with ops.sink_key("gru_l"):
+                E_l = ops.BiGRU2Fn.apply(Utab[2].reshape(T * B, 200), None, T, B, m_l, scale, *self._gru_weights(self.lstm_l))
         Q = sel = pos = None
         if self.use_crn_speaker:
             # k3: shared speaker-party BiGRU over all (modality, dialogue, speaker) sequences at once
             pos, _cnt, sel, rowmap = ops.spk_partition(qmask)
             nseq = 3 * B * S
             m_p = pooled[1] if train_drop else mk.get("gru_p")
-            with ops.gru_tile(tile_p):
+            with ops.gru_tile(tile_p), ops.sink_key("gru_p"):
                 Q = ops.BiGRU2Fn.apply(Utab.reshape(3 * T * B, 200), rowmap, T, nseq, m_p, scale,
                                        *self._gru_weights(self.rnn_parties))
         if side is not None:
@@ -452,7 +455,8 @@ class DialogueGNNModel(nn.Module):
         if pool_gcn:
             gm = {"x": pooled[3], "h0": pooled[4], "layers": pooled[5] if len(gcn.convs) > 0 else None}
         F_ = self.graph_model.forward_stacked(X, geom, gm)
-        log_prob = ops.HeadFn.apply(F_, geom.N, m_h, scale, self.smax_fc.weight, self.smax_fc.bias)
+        with ops.sink_key("head"):
+            log_prob = ops.HeadFn.apply(F_, geom.N, m_h, scale, self.smax_fc.weight, self.smax_fc.bias)
         return log_prob, None, None, None, None
 
     def _forward_relation(self, X, E_l, qmask, geom, seq_lengths, umask, m_h, scale, gated_masks=None):

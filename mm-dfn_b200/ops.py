@@ -27,6 +27,70 @@ def _f32c(t):
     return t.contiguous()
 
 
+def _zeros(n, device, dtype=F32):
+    """zero-filled buffer: torch.empty + one cudaMemsetAsync (a memset node, not a fill kernel)"""
+    t = torch.empty((int(n),), device=device, dtype=dtype)
+    if n:
+        call("mmdfn_memset_zero", t.data_ptr(), int(n) * t.element_size(), stream())
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
+# gradient sink: the data-parallel trainer (dp.FlatAdamTrainer) hands every weight-gradient group of the model a
+# segment of its flat bucket.  Inside `with use_sink(sink)` the backward functions below write their weight gradients
+# straight into those segments (the bucket is zeroed once per step) and return None for them: no per-function zero
+# fills, no gather copy before the all-reduce.  `sink.ready(key)` tells the trainer that a group's gradients are final,
+# so that it can start reducing them while the rest of the backward still runs.
+# ---------------------------------------------------------------------------------------------
+class GradSink:
+    def __init__(self):
+        self.seg = {}            # key -> flat fp32 view of the bucket, laid out as the function's internal buffer
+        self.on_ready = None
+
+    def ready(self, key):
+        if self.on_ready is not None:
+            self.on_ready(key)
+
+
+_SINK = [None]
+_SINK_KEY = [None]
+
+
+class use_sink:
+    def __init__(self, sink):
+        self.sink, self.prev = sink, None
+
+    def __enter__(self):
+        self.prev, _SINK[0] = _SINK[0], self.sink
+
+    def __exit__(self, *exc):
+        _SINK[0] = self.prev
+
+
+class sink_key:
+    """names the gradient group of the Function.apply calls issued inside the block (read in their forward)"""
+
+    def __init__(self, key):
+        self.key, self.prev = key, None
+
+    def __enter__(self):
+        self.prev, _SINK_KEY[0] = _SINK_KEY[0], self.key
+
+    def __exit__(self, *exc):
+        _SINK_KEY[0] = self.prev
+
+
+def _grad_buffer(key, n, device):
+    """(flat buffer of n floats for a function's weight gradients, direct?) -- the sink's segment when one is active"""
+    sink = _SINK[0]
+    if sink is not None and key is not None and key in sink.seg:
+        seg = sink.seg[key]
+        if seg.numel() != n:
+            raise MMDFNError(f"gradient sink segment {key!r} holds {seg.numel()} floats, the function needs {n}")
+        return seg, True
+    return _zeros(n, device), False
+
+
 class DialogGeom:
     """Ragged geometry of one batch: dialogue i owns rows dia_off[i]..dia_off[i+1]-1 of each
     modality third of every (3N, .) array and 3*L_i^2 floats of the block-compact adjacency."""
@@ -225,6 +289,7 @@ class Proj3Fn(torch.autograd.Function):
             call("mmdfn_gemm", 0, 1, rows, 200, K, 1.0, ptr(xs[m]), K, ptr(ws[m]), K, 0.0,
                  U.data_ptr() + m * rows * 200 * 4, 200, ptr(bs[m]), 0, st)
         ctx.save_for_backward(*xs, *ws)
+        ctx.sink_key = _SINK_KEY[0]
         return U
 
     @staticmethod
@@ -236,7 +301,7 @@ class Proj3Fn(torch.autograd.Function):
         st = stream()
         out = [None] * 9
         Ks = [x.shape[2] for x in xs]
-        flat = torch.zeros(200 * sum(Ks) + 600, device=dU.device, dtype=F32)      # all six gradients, one memset
+        flat, direct = _grad_buffer(ctx.sink_key, 200 * sum(Ks) + 600, dU.device)      # all six gradients, one memset
         off = 0
         for m in range(3):
             K = Ks[m]
@@ -250,7 +315,10 @@ class Proj3Fn(torch.autograd.Function):
             off += 200 * K + 200
             call("mmdfn_gemm", 1, 0, 200, K, rows, 1.0, g, 200, ptr(xs[m]), K, 1.0, ptr(dw), K, None, 0, st)
             call("mmdfn_colsum", rows, 200, g, 200, 1.0, ptr(db), st)
-            out[3 + 2 * m], out[4 + 2 * m] = dw, db
+            if not direct:
+                out[3 + 2 * m], out[4 + 2 * m] = dw, db
+        if direct:
+            _SINK[0].ready(ctx.sink_key)
         return tuple(out)
 
 
@@ -316,6 +384,7 @@ class BiGRU2Fn(torch.autograd.Function):
         ws = _empty((query("mmdfn_bigru2_ws_floats", T, nseq, rows),), x.device)
         tab = ptr_table(w)
         ctx.tile = _GRU_TILE[0]
+        ctx.sink_key = _SINK_KEY[0]
         call("mmdfn_gru_set_tile", ctx.tile)
         try:
             call("mmdfn_bigru2_fwd", T, nseq, rows, ptr(x), ptr(rowmap, torch.int32), tab, ptr(mask, U8),
@@ -335,7 +404,7 @@ class BiGRU2Fn(torch.autograd.Function):
         dx = _empty(x.shape, x.device) if ctx.needs_input_grad[0] else None
         # all 16 gradients live in ONE zero-filled buffer (a single memset instead of per-GEMM zero-init launches);
         # weight_ih of the two directions of a layer are adjacent so that one GEMM produces both
-        flat = torch.zeros(sum(t.numel() for t in w), device=x.device, dtype=F32)
+        flat, direct = _grad_buffer(ctx.sink_key, sum(t.numel() for t in w), x.device)
         dw, off = [None] * 16, 0
         for i in _GRU_GRAD_ORDER:
             n = w[i].numel()
@@ -349,6 +418,9 @@ class BiGRU2Fn(torch.autograd.Function):
                  ctx.mask_scale, ptr(y), ptr(dy), ptr(ws), ptr(dx), 0, dtab, 1, ptr(wsb), stream())
         finally:
             call("mmdfn_gru_set_tile", 0)
+        if direct:
+            _SINK[0].ready(ctx.sink_key)
+            return (dx, None, None, None, None, None, *([None] * 16))
         return (dx, None, None, None, None, None, *dw)
 
 
@@ -394,7 +466,7 @@ class PartyPackFn(torch.autograd.Function):
         T, B = ctx.shape
         geom = ctx.geom
         dU = _empty((3, T, B, 200), dX.device)
-        dU[2].zero_()
+        call("mmdfn_memset_zero", dU.data_ptr() + 2 * T * B * 200 * 4, T * B * 200 * 4, stream())      # dU[2] = 0
         dE = _empty((T, B, 200), dX.device)
         dQ = _empty(ctx.q_shape, dX.device) if ctx.q_shape is not None else None
         rows = T * B * 200 * 4
@@ -514,6 +586,7 @@ class GCNStackFn(torch.autograd.Function):
              float(lamda), float(alpha), ptr(W0), ptr(b0), tab, ptr(w_ih), ptr(w_hh), ptr(b_ih), ptr(b_hh),
              ptr(mask_x, U8), ptr(mask_h0, U8), ptr(mask_layers, U8), float(mask_scale), ptr(F_), ptr(ws), stream())
         ctx.save_for_backward(adj_blk, adj_diag, F_, ws, W0, w_ih, w_hh, *convW)
+        ctx.sink_key = _SINK_KEY[0]
         ctx.cfg = (geom, K, int(reason_flag), float(lamda), float(alpha), mask_x, mask_h0, mask_layers, float(mask_scale))
         return F_
 
@@ -530,17 +603,23 @@ class GCNStackFn(torch.autograd.Function):
         d_blk = _empty(adj_blk.shape, dev) if want_adj else None
         d_diag = _empty(adj_diag.shape, dev) if want_adj else None
         if want_adj and K == 0:
-            d_blk.zero_(); d_diag.zero_()
-        # every parameter gradient of the stack lives in ONE zero-filled buffer (a single memset)
-        sizes = [20000, 100, 40000, 40000, 400, 400] + [20000] * K
-        flat = torch.zeros(sum(sizes), device=dev, dtype=F32)
+            call("mmdfn_memset_zero", d_blk.data_ptr(), d_blk.numel() * 4, stream())
+            call("mmdfn_memset_zero", d_diag.data_ptr(), d_diag.numel() * 4, stream())
+        # every parameter gradient of the stack lives in ONE zero-filled buffer (a single memset, or the trainer's
+        # bucket segment); the LSTM's four tensors are part of it only when the gate is in use
+        use_rnn = bool(reason_flag) and K > 0
+        sizes = [20000, 100] + ([40000, 40000, 400, 400] if use_rnn else []) + [20000] * K
+        flat, direct = _grad_buffer(ctx.sink_key, sum(sizes), dev)
         views, off = [], 0
         for n in sizes:
             views.append(flat[off:off + n])
             off += n
         dW0, db0 = views[0].view(100, 200), views[1]
-        dw_ih, dw_hh, db_ih, db_hh = views[2].view(400, 100), views[3].view(400, 100), views[4], views[5]
-        dconv = [v.view(200, 100) for v in views[6:]]
+        if use_rnn:
+            dw_ih, dw_hh, db_ih, db_hh = views[2].view(400, 100), views[3].view(400, 100), views[4], views[5]
+        else:
+            dw_ih = dw_hh = db_ih = db_hh = None
+        dconv = [v.view(200, 100) for v in views[(6 if use_rnn else 2):]]
         wsb = _empty((query("mmdfn_gcn_stack_bwd_ws_floats", n3, K),), dev)
         tab = ptr_table(convW) if K > 0 else None
         dtab = ptr_table(dconv) if K > 0 else None
@@ -548,9 +627,11 @@ class GCNStackFn(torch.autograd.Function):
              tab, ptr(w_ih), ptr(w_hh), ptr(mask_x, U8), ptr(mask_h0, U8), ptr(mask_layers, U8), mask_scale,
              ptr(F_), ptr(ws), ptr(dF), ptr(dX), ptr(d_blk), ptr(d_diag), ptr(dW0), ptr(db0), dtab, ptr(dw_ih),
              ptr(dw_hh), ptr(db_ih), ptr(db_hh), 1, ptr(wsb), stream())
-        if not reason_flag or K == 0:
-            # the reference never touches the LSTM on this configuration: its grads stay None and Adam skips the weights
-            dw_ih = dw_hh = db_ih = db_hh = None
+        # (reason_flag off or K == 0: the reference never touches the LSTM -- its grads stay None and Adam skips the weights)
+        if direct:
+            _SINK[0].ready(ctx.sink_key)
+            return (dX, d_blk, d_diag, None, None, None, None, None, None, None, None, None,
+                    None, None, None, None, None, None, *([None] * K))
         return (dX, d_blk, d_diag, None, None, None, None, None, None, None, None, None,
                 dW0, db0, dw_ih, dw_hh, db_ih, db_hh, *dconv)
 
@@ -570,6 +651,7 @@ class HeadFn(torch.autograd.Function):
         call("mmdfn_head_fwd", N, C, ptr(F_), ptr(mask, U8), float(mask_scale), int(relu), ptr(Wc), ptr(bc), ptr(R), ptr(lp),
              stream())
         ctx.save_for_backward(R, lp, Wc)
+        ctx.sink_key = _SINK_KEY[0]
         ctx.mask, ctx.mask_scale, ctx.N, ctx.relu = mask, float(mask_scale), N, int(relu)
         return lp
 
@@ -580,11 +662,14 @@ class HeadFn(torch.autograd.Function):
         dev = R.device
         dlp = _f32c(dlp)
         dF = _empty(R.shape, dev)
-        flat = torch.zeros(C * 900 + C, device=dev, dtype=F32)
+        flat, direct = _grad_buffer(ctx.sink_key, C * 900 + C, dev)
         dWc, dbc = flat[:C * 900].view(C, 900), flat[C * 900:]
         scratch = _empty((max(N, 1), C), dev)
         call("mmdfn_head_bwd", N, C, ptr(ctx.mask, U8), ctx.mask_scale, ctx.relu, ptr(Wc), ptr(R), ptr(lp), ptr(dlp), ptr(dF),
              ptr(dWc), ptr(dbc), 1, ptr(scratch), stream())
+        if direct:
+            _SINK[0].ready(ctx.sink_key)
+            return dF, None, None, None, None, None, None
         return dF, None, None, None, dWc, dbc, None
 
 

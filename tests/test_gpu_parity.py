@@ -39,9 +39,19 @@ def relerr(a, b):
 # ---------------------------------------------------------------------------------------------
 # GEMM / colsum
 # ---------------------------------------------------------------------------------------------
+@pytest.fixture(params=[0, 1, 2], autouse=False)
+def gemm_variant(request):
+    """0 = default dispatch (second-generation tcgen05 kernel for aligned NT problems), 1 = first generation only,
+    2 = second generation for every eligible form (its NN / TN operand paths: TMA raw ring + transposed reads)"""
+    from mmdfn_b200 import _lib
+    _lib.call("mmdfn_gemm_tc_set_variant", request.param)
+    yield request.param
+    _lib.call("mmdfn_gemm_tc_set_variant", 0)
+
+
 @pytest.mark.parametrize("M,N,K", [(1, 1, 1), (37, 6, 900), (300, 200, 1582), (257, 300, 200), (5000, 600, 200),
-                                   (20000, 200, 342), (64, 64, 16), (129, 65, 17)])
-def test_gemm_nt_bias_relu(M, N, K):
+                                   (20000, 200, 342), (64, 64, 16), (129, 65, 17), (3200, 200, 1024), (9600, 400, 100)])
+def test_gemm_nt_bias_relu(M, N, K, gemm_variant):
     _, ops, L = _mods()
     a, b, bias = rnd(M, K, seed=1), rnd(N, K, seed=2), rnd(N, seed=3)
     c0 = rnd(M, N, seed=4)
@@ -51,8 +61,8 @@ def test_gemm_nt_bias_relu(M, N, K):
     assert maxerr(C, ref) < 1e-4 * max(1.0, math.sqrt(K) / 4)     # fp32 accumulate, |x| ~ sqrt(K)
 
 
-@pytest.mark.parametrize("M,N,K", [(100, 200, 300), (777, 100, 400), (3, 5, 7), (20000, 300, 200)])
-def test_gemm_nn(M, N, K):
+@pytest.mark.parametrize("M,N,K", [(100, 200, 300), (777, 100, 400), (3, 5, 7), (20000, 300, 200), (9600, 200, 100), (9601, 204, 37)])
+def test_gemm_nn(M, N, K, gemm_variant):
     _, ops, L = _mods()
     a, b = rnd(M, K, seed=5), rnd(K, N, seed=6)
     A, B = a.to(DEV), b.to(DEV)
@@ -61,8 +71,9 @@ def test_gemm_nn(M, N, K):
     assert maxerr(C, a.double() @ b.double()) < 1e-4 * max(1.0, math.sqrt(K) / 4)
 
 
-@pytest.mark.parametrize("M,N,K", [(300, 200, 50000), (200, 1582, 3000), (6, 300, 1623), (100, 100, 9), (400, 100, 76800)])
-def test_gemm_tn_splitk(M, N, K):
+@pytest.mark.parametrize("M,N,K", [(300, 200, 50000), (200, 1582, 3000), (6, 300, 1623), (100, 100, 9), (400, 100, 76800),
+                                   (200, 1024, 3200), (132, 116, 9603)])
+def test_gemm_tn_splitk(M, N, K, gemm_variant):
     """weight-gradient shape: C[M,N] = A^T B with a long contraction (split-K + atomics), beta = 1"""
     _, ops, L = _mods()
     a, b, c0 = rnd(K, M, seed=7, scale=0.1), rnd(K, N, seed=8, scale=0.1), rnd(M, N, seed=9)

@@ -39,6 +39,8 @@ def stamps(lengths, detail=False):
     if detail:
         t0 = d[0]
         ng = min(60, -(-lengths[0] // 8) + 13) if L.query('mmdfn_gcn_layer_img_floats') < 25000 else min(60, -(-lengths[0] // 16) + 7)
+        print("   phase A chunk 3: A stores +%d  B pieces +%d  fence +%d  syncwarp +%d  arrive +%d" % tuple(d[241 + i] - d[240 + i] for i in range(5)))
+        print("   phase B chunk 3: A stores +%d  W stores +%d  fence +%d  syncwarp+arrive +%d" % tuple(d[249 + i] - d[248 + i] for i in range(4)))
         print("   k-step: issuer-full | conv-reached-wait | conv-stage-free   (cycles since entry)")
         for g in range(ng):
             print("   %2d: %6d | %6d | %6d" % (g, d[64 + g] - t0, d[192 + g] - t0, d[128 + g] - t0))
