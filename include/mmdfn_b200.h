@@ -59,6 +59,9 @@ int mmdfn_gemm_tc_set_variant(int v);
 int mmdfn_umma_probe(float* out, int N, int lbo, int sbo, int mn_major, int probe_a, void* stream);
 /* debug aid: one product with the A operand in tensor memory; out (128 x 16) must read back 16 m + n */
 int mmdfn_umma_probe_ta(float* out, int a_col, void* stream);
+/* debug aid: cycles for `reps` and 2*reps back-to-back 128 x N MMAs (kind 0 = tf32, 1 = bf16; A from smem or tensor
+ * memory; `issuers` threads of different warps issue concurrently into separate accumulators) */
+int mmdfn_umma_rate(long long* out, int kind, int N, int a_tmem, int reps, int issuers, void* stream);
 /* zero-fill `bytes` bytes at p with cudaMemsetAsync on `stream` (gradient buffers: a memset node instead of a fill kernel) */
 int mmdfn_memset_zero(void* p, long long bytes, void* stream);
 /* out[n] = beta*out[n] + sum_m A[m*lda+n]   (bias gradients) */
@@ -162,8 +165,10 @@ int mmdfn_gcn_layer_fwd(int B, int N, int Lmax, const int* dia_off, const long l
 int mmdfn_gcn_layer_bwd(int B, int N, int Lmax, const int* dia_off, const long long* blk_off, const float* adj_blk,
                         const float* adj_diag, const float* du, long long ldu, const float* wimg_t, float* t_out,
                         long long ldt, const float* add, float* out, void* stream);
-/* timing aid (process-global, like mmdfn_adj_spmm_set_variant): 0 = 16-wide K chunks / 2 operand stages (default),
- * 1 = 8-wide chunks / 3 stages.  Weight images must be (re)built by mmdfn_gcn_layer_prep under the same setting. */
+/* timing aid (process-global, like mmdfn_adj_spmm_set_variant): 0 = default (second-generation persistent kernel with
+ * tensor-memory A operands for batches whose dialogues have <= 128 utterances, first generation with 16-wide K chunks
+ * otherwise), 1 = first generation, 8-wide chunks / 3 stages, 2 = first generation, 16-wide chunks / 2 stages.  Weight
+ * images must be (re)built by mmdfn_gcn_layer_prep under the same setting. */
 int mmdfn_gcn_layer_set_variant(int v);
 /* profiling aid: 256 x int64 device buffer receiving clock64() stamps of CTA (0,0) (NULL switches it off) */
 int mmdfn_gcn_layer_set_debug(long long* device_buf);

@@ -25,6 +25,7 @@
 // shared memory and 256 TMEM columns per CTA -> two CTAs per SM, so one tile's loads/epilogues overlap the other's MMAs.
 #include "umma.cuh"
 #include "internal.cuh"
+#include "gcn_layer.cuh"
 #include <math.h>
 
 namespace mmdfn {
@@ -61,32 +62,6 @@ struct GLGeo {
 // default configuration (see gcn_layer_variant): 16-wide chunks, 2 stages
 constexpr int GL_KC0 = 16, GL_NS0 = 2;
 constexpr int GL_KC1 = 8, GL_NS1 = 3;
-
-struct GcnLayerArgs {
-  int B, N;
-  const int* dia_off;
-  const i64* blk_off;
-  const float* adj_blk;
-  const float* adj_diag;
-  const float* zin; i64 ldz;          // (3N, 100) rows, row stride ldz floats (multiple of 4)
-  const float* wimg;                  // pre-split weight operand of phase B (GLGeo::IMG floats)
-  float* t_out; i64 ldt;              // optional: T rows
-  // forward epilogue
-  const float* r; i64 ldr;            // R rows (h0 Mbot)
-  const float* q;                     // optional residual rows (ld 100)
-  const unsigned char* mask;          // optional keep mask (3N x 100)
-  float scale;
-  unsigned char* flags;               // out: relu-and-keep flags (3N x 100)
-  // both
-  const float* add;                   // backward: optional rows added to the result (ld 100)
-  float* out; i64 ldo;
-  long long* dbg;
-};
-
-__device__ __forceinline__ void gl_split(float x, float& hi, float& lo) {
-  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-  lo = x - hi;
-}
 
 __device__ __forceinline__ void gl_split_store(const float4 v, uint8_t* hi_dst, uint8_t* lo_dst) {
   float4 h, l;
@@ -566,9 +541,11 @@ __global__ void gcn_unfold_kernel(GcnUnfoldArgs p) {
 }
 
 static long long* g_gl_dbg = nullptr;
-// 0 = 16-wide K chunks, 2 operand stages (default); 1 = 8-wide chunks, 3 stages.  Process-global timing knob (tools/):
-// the weight images are laid out for the configuration that was current when gcn_layer_prep built them.
+// First-generation configuration: 0 = 16-wide K chunks, 2 operand stages; 1 = 8-wide chunks, 3 stages.  Process-global
+// timing knob (tools/): the weight images are laid out for the configuration that was current when gcn_layer_prep built
+// them.  g_gl_gen2: use the second-generation kernel (gcn_layer2.cu, same 16-wide image) wherever it is eligible.
 static int g_gl_variant = 0;
+static bool g_gl_gen2 = true;
 
 long long gcn_layer_img_floats() { return g_gl_variant == 0 ? GLGeo<GL_KC0, GL_NS0>::IMG : GLGeo<GL_KC1, GL_NS1>::IMG; }
 
@@ -641,6 +618,7 @@ static int launch_layer_cfg(const GcnLayerArgs& a, int Lmax, cudaStream_t st) {
 
 template <bool FWD>
 static int launch_layer(const GcnLayerArgs& a, int Lmax, cudaStream_t st) {
+  if (g_gl_gen2 && g_gl_variant == 0 && gcn_layer2_eligible(Lmax)) return gcn_layer2_launch(FWD, a, Lmax, st);
   return g_gl_variant == 0 ? launch_layer_cfg<FWD, GL_KC0, GL_NS0>(a, Lmax, st) : launch_layer_cfg<FWD, GL_KC1, GL_NS1>(a, Lmax, st);
 }
 
@@ -679,8 +657,9 @@ int gcn_layer_bwd(int B, int N, int Lmax, const int* dia_off, const i64* blk_off
 extern "C" long long mmdfn_gcn_layer_img_floats(void) { return mmdfn::gcn_layer_img_floats(); }
 
 extern "C" int mmdfn_gcn_layer_set_variant(int v) {
-  if (v < 0 || v > 1) return MMDFN_EINVAL;
-  mmdfn::g_gl_variant = v;
+  if (v < 0 || v > 2) return MMDFN_EINVAL;
+  mmdfn::g_gl_variant = v == 1 ? 1 : 0;
+  mmdfn::g_gl_gen2 = v == 0;
   return 0;
 }
 

@@ -101,7 +101,88 @@ __global__ void __launch_bounds__(128, 1) umma_probe_ta_kernel(float* out, int a
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, 256);
 }
+
+// Third probe: issue rate of back-to-back tcgen05.mma instructions (operands are zeros; only the timing matters).
+// kind 0 = tf32 (K = 8), 1 = bf16 (kind::f16, K = 16); A from shared memory or tensor memory; `issuers` threads (lane 0
+// of warps 0..issuers-1) issue concurrently, each into its own accumulator (columns 64 w, N <= 64 when issuers > 1).
+// out[0] = cycles until every issuer's `reps` MMAs completed, out[1] = the same for 2 * reps.
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(long long* out, int kind, int N, int a_tmem, int reps, int issuers) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar[4];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 0.f;
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) { for (int i = 0; i < 4; i++) umma::mbar_init(&bar[i], 1); umma::fence_barrier_init(); }
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  {
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 256;
+    for (int c = 0; c < 128; c += 8)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr + c), "r"(0u) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  uint32_t parity = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    const int n = reps << pass;
+    __syncthreads();
+    const long long t0 = clock64();
+    if (lane == 0 && warp < issuers) {
+      const uint32_t base = umma::smem_u32(smem);
+      const uint32_t idesc = (1u << 4) | ((kind == 0 ? 2u : 1u) << 7) | ((kind == 0 ? 2u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+      const uint64_t adesc = umma::smem_desc(base, 128, 528);
+      const uint64_t bdesc = umma::smem_desc(base + 16384, 128, 528);
+      const uint32_t tmem_d = tmem + (uint32_t)(issuers > 1 ? 64 * warp : 0);
+      const uint32_t tmem_a = tmem + 256 + 32 * warp;
+      if (a_tmem) {
+        if (kind == 0) {
+          for (int i = 0; i < n; i++) umma::mma_tf32_ta(tmem_d, tmem_a, bdesc, idesc, i > 0 ? 1u : 0u);
+        } else {
+          for (int i = 0; i < n; i++)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(i > 0 ? 1u : 0u) : "memory");
+        }
+      } else {
+        if (kind == 0) {
+          for (int i = 0; i < n; i++) umma::mma_tf32(tmem_d, adesc, bdesc, idesc, i > 0 ? 1u : 0u);
+        } else {
+          for (int i = 0; i < n; i++)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(i > 0 ? 1u : 0u) : "memory");
+        }
+      }
+      umma::mma_commit(&bar[warp]);
+      umma::mbar_wait(&bar[warp], parity);
+    }
+    parity ^= 1;
+    __syncthreads();
+    if (tid == 0) out[pass] = clock64() - t0;
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
 }  // namespace mmdfn
+
+extern "C" int mmdfn_umma_rate(long long* out, int kind, int N, int a_tmem, int reps, int issuers, void* stream) {
+  using namespace mmdfn;
+  if (!out) return MMDFN_ENULL;
+  if (kind < 0 || kind > 1 || N < 16 || N > 256 || (N & 15) || reps < 1 || issuers < 1 || issuers > 4 || (issuers > 1 && N > 64)) return MMDFN_EINVAL;
+  static bool configured = false;
+  if (!configured) {
+    MMDFN_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    configured = true;
+  }
+  umma_rate_kernel<<<1, 128, 65536, (cudaStream_t)stream>>>(out, kind, N, a_tmem, reps, issuers);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int mmdfn_umma_probe_ta(float* out, int a_col, void* stream) {
   using namespace mmdfn;

@@ -360,8 +360,9 @@ def layer_variant(request):
     _lib.call("mmdfn_gcn_layer_set_variant", 0)
 
 
-@pytest.mark.parametrize("layer_variant", [0, 1], indirect=True)
-@pytest.mark.parametrize("lengths", [[5, 3, 7], [100, 100], [128, 1, 37, 64, 99, 33, 2], [129, 16], [300, 17], [500]])
+@pytest.mark.parametrize("layer_variant", [0, 1, 2], indirect=True)     # 0: second-generation kernel where eligible; 1, 2: first generation
+@pytest.mark.parametrize("lengths", [[5, 3, 7], [100, 100], [128, 1, 37, 64, 99, 33, 2], [104, 8, 96, 112, 120, 12], [129, 16], [300, 17], [500],
+                                     [100] * 60 + [57, 3]])
 def test_fused_graph_conv_layer_forward_and_backward_kernels(lengths, layer_variant):
     """mmdfn_gcn_layer_fwd / _bwd through the C ABI against the oracle's GraphConvolution (code/model_GCN.py:176-189)
     + ReLU / dropout / residual of the stack loop (:469-472), and against fp64 dense products for the backward form."""
