@@ -182,36 +182,29 @@ __global__ void __launch_bounds__(GL_THREADS, 2) gcn_layer_kernel(GcnLayerArgs p
     // ===== MMA issuer (lane 0) + z producer (lanes 0..15) =====
     for (int zc = 0; zc < GL_ZR && zc < nzc; zc++) issue_z(zc, lane);
     const int total = nchA + WCHUNKS;
+    const uint64_t d0 = umma::smem_desc(umma::smem_u32(stages), GL_LBO, SBO);
+    const uint32_t dhi = (uint32_t)(d0 >> 32), dlo = (uint32_t)d0;
     for (int g = 0; g < total; g++) {
       const int s = g % NS;
-      if (lane == 0) {
-        umma::mbar_wait(&bar_full[s], (uint32_t)((g / NS) & 1));
-        umma::tc_fence_after_sync();
-        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && g < 60) p.dbg[64 + g] = clock64();   // issuer: chunk g full
-      }
-      __syncwarp();
+      umma::mbar_wait(&bar_full[s], (uint32_t)((g / NS) & 1));           // the whole warp: the MMA issue below is convergent
+      umma::tc_fence_after_sync();
+      if (lane == 0 && p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && g < 60) p.dbg[64 + g] = clock64();   // issuer: chunk g full
       // chunk g read the LAST rows of raw chunk zc: every converter has finished with that ring slot (it arrived on
       // bar_full after its reads) -> refill it with the raw chunk one ring revolution ahead
       if (g < nchA && ((g + 1) * KC) % GL_ZROWS == 0) {
         const int zc = ((g + 1) * KC) / GL_ZROWS - 1;
         if (zc + GL_ZR < nzc) issue_z(zc + GL_ZR, lane);
       }
-      if (lane == 0) {
-        const uint32_t base = umma::smem_u32(stages + s * STAGE);
-#pragma unroll
-        for (int j = 0; j < KC / 8; j++) {
-          const uint64_t a_hi = umma::smem_desc(base + j * 2 * GL_LBO, GL_LBO, SBO);
-          const uint64_t a_lo = umma::smem_desc(base + A_PART + j * 2 * GL_LBO, GL_LBO, SBO);
-          const uint64_t b_hi = umma::smem_desc(base + 2 * A_PART + j * 2 * GL_LBO, GL_LBO, SBO);
-          const uint64_t b_lo = umma::smem_desc(base + 2 * A_PART + B_PART + j * 2 * GL_LBO, GL_LBO, SBO);
-          const uint32_t acc = ((g > 0 && g != nchA) || j > 0) ? 1u : 0u;      // each phase starts a fresh accumulator
-          umma::mma_tf32(tmem, a_hi, b_hi, IDESC, acc);
-          umma::mma_tf32(tmem + GL_CORR, a_lo, b_hi, IDESC, acc);
-          umma::mma_tf32(tmem + GL_CORR, a_hi, b_lo, IDESC, 1u);
-        }
-        umma::mma_commit(&bar_free[s]);
-      }
       __syncwarp();
+      const uint32_t o = dlo + (uint32_t)s * (STAGE >> 4);
+#pragma unroll
+      for (int j = 0; j < KC / 8; j++) {
+        const uint32_t oj = o + (uint32_t)j * ((2 * GL_LBO) >> 4);
+        // each phase starts a fresh accumulator
+        umma::kstep3_elect(tmem, tmem + GL_CORR, dhi, oj, oj + (A_PART >> 4), oj + ((2 * A_PART) >> 4), oj + ((2 * A_PART + B_PART) >> 4),
+                           IDESC, ((g > 0 && g != nchA) || j > 0) ? 1u : 0u);
+      }
+      umma::mma_commit_elect(&bar_free[s]);
     }
     umma::tc_fence_before_sync();
     __syncthreads();

@@ -6,20 +6,31 @@
 //   phase B   U = T . Mw
 //   forward   z_out = dropout(relu(U + R)) (+ q), flags;      backward   d_in = U (+ add), T rows written out
 //
-// What changed against the first generation (round-2 phase stamps: 32 k cycles per tile, the tensor pipe ~117 cycles per
-// 128x112x8 MMA because BOTH operands came from shared memory, every row operand fetched by latency-bound LDG batches):
+// What changed against the first generation (round-2 phase stamps: 32 k cycles per tile; ~117 cycles per 128x112x8 MMA
+// because the issuing lane rebuilt descriptors inside a lane-0 branch; every row operand fetched by latency-bound LDG
+// batches; a tile's phases strictly one after the other):
 //   * the A operand of both products lives in TENSOR MEMORY (tcgen05.mma [d], [a_tmem], b_desc): the raw A_hat block
 //     arrives by ONE TMA bulk copy, each thread reads its own row (conflict-free 128-bit reads), splits it into tf32
 //     hi/lo and tcgen05.st's it; the phase-A result T goes TMEM -> registers (+ cross terms) -> hi/lo -> TMEM without
 //     touching shared memory.  Only the B operand is fetched from shared memory by the tensor core.
-//   * every row operand (cross-modal z rows, R, q, add; the out / T rows on the way back) moves by TMA bulk copies
-//     through two row buffers: no LSU traffic, no exposed latency; the weight image streams into the operand ring by
-//     bulk copies as well (one 14.8 KB copy per 16-wide K chunk).
-//   * roles: 8 row warps (thread = tile row: cross-term hop, fused epilogue), 8 converter warps (A_hat -> TMEM, z ->
-//     transposed hi/lo ring stages straight from global memory, three chunks of loads in flight), one MMA issuer, two
-//     TMA producers.  The CTA walks tiles t = blockIdx.x, += gridDim.x; the next tile's loads and conversions overlap
-//     the current tile's MMAs and epilogue.
+//   * every row operand (cross-modal z rows, R, q, add, the keep mask; the out / T rows and the flag bytes on the way
+//     back) moves by TMA bulk copies through two row buffers, issued by a producer warp: no LSU traffic, no exposed
+//     latency in the compute warps; the pre-split weight image streams into the operand ring by bulk copies as well
+//     (one 14.8 KB copy per 16-wide K chunk).
+//   * the MMA warp runs its loop convergently with uniform operands and one elected lane issues: ~54 cycles per MMA
+//     (= the tensor time, tools/umma_rate.py) instead of ~117.
+//   * everything is pipelined per 16-column K chunk: phase B starts on T chunk c as soon as the hop has produced it
+//     (after the accumulators were read out completely -- they are also phase B's destination), the NEXT tile's A_hat
+//     chunk c is written as soon as phase B has consumed T chunk c, its z chunks are converted while phase B still
+//     runs, and its phase A starts the moment the epilogue has drained the accumulators into registers.
+//   * roles: 8 row warps (thread = tile row x column half: hop, epilogue), 4 A warps (A_hat -> TMEM), 4 z warps (z ->
+//     transposed hi/lo ring stages: 4 x 4 blocks, four coalesced 128-bit loads, register transpose), one MMA warp, one
+//     row-operand producer (loads AND stores), one weight-chunk producer.  The CTA walks tiles t = blockIdx.x,
+//     += gridDim.x.
 // Accuracy is unchanged (3-term tf32 split, separate main / correction accumulators in TMEM).
+// Measured (B200, profiles/r02_gcn_layer2_*): 13.4 us per launch at the 32-dialogue bench shard (first generation 25.7),
+// 56 us at 256 dialogues (96), 97 us at 512 (179); per-tile critical loop ~13.7 k cycles (hop + phase B 5.9 k, epilogue
+// 4.4 k, out store -> next cross-row load through the shared row buffers 3.3 k).
 #include "umma.cuh"
 #include "internal.cuh"
 #include "gcn_layer.cuh"
@@ -32,6 +43,9 @@ constexpr int L2_LBO = 128, L2_SBO = 528;
 constexpr int L2_BPART = (L2_BN / 8) * L2_SBO;             // 7392 B: one B part (hi or lo) of a 16-wide K chunk
 constexpr int L2_STAGE = 2 * L2_BPART;                     // 14784 B = one chunk of the pre-split weight image
 constexpr int L2_WCHUNKS = 7;                              // K chunks of the 100-deep second product (13 k-steps of 8)
+// Phase B consumes its K chunks in the order 0 3 1 4 2 5 6: the hop's two column halves (chunks 0-2 / 3-6) finish their
+// chunks at the same pace, so alternating between them lets the tensor core follow the hop instead of waiting for one half.
+__host__ __device__ constexpr int l2_bchunk(int i) { return i == 6 ? 6 : (i >> 1) + 3 * (i & 1); }
 constexpr int L2_ROWW = 8, L2_CONVW = 8;
 constexpr int L2_W_MMA = 16, L2_W_PA = 17, L2_W_PW = 18;
 constexpr int L2_THREADS = 19 * 32;
@@ -110,6 +124,12 @@ __device__ __forceinline__ void split_st8(uint32_t tlane, uint32_t col, const fl
 }
 
 struct Tile { int b, m, off, L; };
+// keep mask / flag bytes of a tile (100 L contiguous bytes at byte offset 100 row0) can move by TMA bulk copies when that
+// range is 16-byte aligned and a multiple of 16 bytes; otherwise the row warps copy them with plain 32-bit accesses
+__device__ __forceinline__ bool mask_by_tma(const GcnLayerArgs& p, i64 row0, int L) {
+  return ((L & 3) == 0) && ((row0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.flags) & 15) == 0) &&
+         (p.mask == nullptr || (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0);
+}
 __device__ __forceinline__ Tile tile_of(const GcnLayerArgs& p, int t) {
   Tile x;
   x.b = t / 3;
@@ -138,13 +158,13 @@ __global__ void __launch_bounds__(L2_THREADS, 1) gcn_layer2_kernel(GcnLayerArgs 
       umma::mbar_init(&bars[BAR_FULL + s], 4);                // a z chunk: the 4 warps of one converter group; a weight chunk: 3 + expect_tx
       umma::mbar_init(&bars[BAR_FREE + s], 1);
     }
-    for (int c = 0; c < 8; c++) umma::mbar_init(&bars[BAR_A_RDY + c], L2_CONVW);
+    for (int c = 0; c < 8; c++) umma::mbar_init(&bars[BAR_A_RDY + c], 4);
     for (int c = 0; c < 7; c++) {
       umma::mbar_init(&bars[BAR_T_RDY + c], 4);
       umma::mbar_init(&bars[BAR_T_USED + c], 1);
     }
     umma::mbar_init(&bars[BAR_ARAW_FULL], 1);
-    umma::mbar_init(&bars[BAR_ARAW_FREE], L2_CONVW);
+    umma::mbar_init(&bars[BAR_ARAW_FREE], 4);
     umma::mbar_init(&bars[BAR_MMA_A], 1);
     umma::mbar_init(&bars[BAR_MMA_B], 1);
     umma::mbar_init(&bars[BAR_D_FREE], L2_ROWW);
@@ -172,21 +192,36 @@ __global__ void __launch_bounds__(L2_THREADS, 1) gcn_layer2_kernel(GcnLayerArgs 
     const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
     uint32_t xyc = 0;
     int it = 0;
+    // geometry and the two cross-modal diagonal entries of this thread's row are fetched one tile ahead (during the
+    // previous tile's epilogue), so that the hop can start the moment phase A completes
+    auto diag_of = [&](const Tile& x, float& d1, float& d2) {
+      const int o1 = (x.m == 0) ? 1 : 0, o2 = (x.m == 2) ? 1 : 2;
+      d1 = d2 = 0.f;
+      if (row < x.L) {
+        d1 = __ldg(p.adj_diag + (i64)(min(x.m, o1) + max(x.m, o1) - 1) * p.N + x.off + row);
+        d2 = __ldg(p.adj_diag + (i64)(min(x.m, o2) + max(x.m, o2) - 1) * p.N + x.off + row);
+      }
+    };
+    Tile tn = tile_of(p, min((int)blockIdx.x, ntiles - 1));
+    float e1n, e2n;
+    diag_of(tn, e1n, e2n);
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
-      const Tile tl = tile_of(p, t);
+      const Tile tl = tn;
+      const float e1 = e1n, e2 = e2n;
       const int L = tl.L, m = tl.m;
       const i64 row0 = (i64)m * p.N + tl.off;
       const bool rv = row < L;
-      const int o1 = (m == 0) ? 1 : 0, o2 = (m == 2) ? 1 : 2;
-      float e1 = 0.f, e2 = 0.f;
-      if (rv) {
-        e1 = __ldg(p.adj_diag + (i64)(min(m, o1) + max(m, o1) - 1) * p.N + tl.off + row);
-        e2 = __ldg(p.adj_diag + (i64)(min(m, o2) + max(m, o2) - 1) * p.N + tl.off + row);
-      }
       const int nw = 25 * L;                                   // 32-bit words of the tile's keep mask / flags
-      if (FWD && p.mask) {
+      const bool mtma = mask_by_tma(p, row0, L);
+      if (FWD && p.mask && !mtma) {
+        // 25 L <= 3200 words over 256 threads: at most 13 per thread, all loads issued before the first store
         const uint32_t* mg = reinterpret_cast<const uint32_t*>(p.mask + row0 * L2_G);
-        for (int w = tid; w < nw; w += 256) mask_s[w] = __ldg(mg + w);
+        uint32_t mv[13];
+#pragma unroll
+        for (int i = 0; i < 13; i++) mv[i] = (tid + 256 * i < nw) ? __ldg(mg + tid + 256 * i) : 0u;
+#pragma unroll
+        for (int i = 0; i < 13; i++)
+          if (tid + 256 * i < nw) mask_s[tid + 256 * i] = mv[i];
       }
       float* xr = X + row * L2_G;
       const float* yr = Y + row * L2_G;
@@ -248,19 +283,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) gcn_layer2_kernel(GcnLayerArgs 
       if (!FWD) umma::fence_proxy_async_smem();
       L2_STAMP(tid == 0, 3);
       row_bar_sync();                                           // every row warp is done with the cross rows
-      if (warp == 0) {
-        if (!FWD) {
-          float* dst = p.t_out + row0 * p.ldt;
-          if (p.ldt == L2_G) {
-            if (lane == 0) bulk_s2g(dst, X, 400u * L);
-          } else {
-            for (int r = lane; r < L; r += 32) bulk_s2g(dst + (i64)r * p.ldt, X + r * L2_G, 400u);
-          }
-          bulk_commit_wait_read();
-          __syncwarp();
-        }
-        if (lane == 0) mbar_arrive(&bars[BAR_XY_FREE]);
-      }
+      if (tid == 0) mbar_arrive(&bars[BAR_XY_FREE]);          // the row-operand producer stores the T rows (backward) and reloads
       // ---------------- epilogue ----------------
       L2_STAMP(tid == 0, 4);
       umma::mbar_wait(&bars[BAR_MMA_B], (uint32_t)(it & 1));
@@ -284,6 +307,10 @@ __global__ void __launch_bounds__(L2_THREADS, 1) gcn_layer2_kernel(GcnLayerArgs 
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[BAR_D_FREE]);            // accumulators drained: the next tile's phase A may start
       L2_STAMP(tid == 0, 6);
+      if (t + (int)gridDim.x < ntiles) {
+        tn = tile_of(p, t + gridDim.x);
+        diag_of(tn, e1n, e2n);
+      }
       umma::mbar_wait(&bars[BAR_X_FULL], xyc & 1);
       umma::mbar_wait(&bars[BAR_Y_FULL], xyc & 1);
       xyc++;
@@ -299,14 +326,14 @@ __global__ void __launch_bounds__(L2_THREADS, 1) gcn_layer2_kernel(GcnLayerArgs 
               if (FWD) {
                 const float4 r4 = *reinterpret_cast<const float4*>(xr + c);
                 const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
-                const uint32_t mk = p.mask ? mask_s[row * 25 + (c >> 2)] : 0x01010101u;
+                const uint32_t mk = p.mask ? mask_s[row * 25 + (c >> 2)] : 0x01010101u;       // keep bytes are 0 / 1
                 uint32_t fl = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                  const float val = o[j] + rr[j];
-                  const bool on = (val > 0.f) && ((mk >> (8 * j)) & 0xFFu);
-                  o[j] = on ? val * p.scale : 0.f;
-                  fl |= (on ? 1u : 0u) << (8 * j);
+                  // relu, then keep * scale as ONE factor; the result is +0 or positive, so "kept and positive" is "bits != 0"
+                  const float ks = (float)((mk >> (8 * j)) & 0xFFu) * p.scale;
+                  o[j] = fmaxf(o[j] + rr[j], 0.f) * ks;
+                  fl |= min(__float_as_uint(o[j]), 1u) << (8 * j);
                 }
                 if (p.q) {
                   const float4 q4v = *reinterpret_cast<const float4*>(yr + c);
@@ -326,34 +353,86 @@ __global__ void __launch_bounds__(L2_THREADS, 1) gcn_layer2_kernel(GcnLayerArgs 
       umma::fence_proxy_async_smem();
       row_bar_sync();
       L2_STAMP(tid == 0, 9);
-      if (FWD) {
+      if (FWD && !mtma) {
         uint32_t* fg = reinterpret_cast<uint32_t*>(p.flags + row0 * L2_G);
         for (int w = tid; w < nw; w += 256) fg[w] = mask_s[w];
       }
-      if (warp == 0) {
-        float* dst = p.out + row0 * p.ldo;
-        if (p.ldo == L2_G) {
-          if (lane == 0) bulk_s2g(dst, X, 400u * L);
-        } else {
-          for (int r = lane; r < L; r += 32) bulk_s2g(dst + (i64)r * p.ldo, X + r * L2_G, 400u);
-        }
-        bulk_commit_wait_read();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[BAR_XY_FREE]);
-      }
+      if (tid == 0) mbar_arrive(&bars[BAR_XY_FREE]);          // the row-operand producer stores the out rows
       L2_STAMP(tid == 0, 10);
     }
-  } else if (warp < L2_ROWW + L2_CONVW) {
-    // ============================== converter warps ==============================
-    // (a) A_hat block -> TMEM, one 16-column K chunk at a time: thread = tile row, group kh takes the chunk's kh-th 8-column
-    //     block; chunk c of the NEXT tile may be written as soon as the current tile's phase B has consumed T chunk c.
-    // (b) z block -> B operand of phase A: group (c & 1) converts chunk c.  A thread loads a 4 x 4 block (rows k..k+3,
-    //     columns 4 cg..4 cg+3) with four coalesced 128-bit loads, transposes it in registers and stores four pieces.
-    const int cw = warp - L2_ROWW, ctid = tid - 32 * L2_ROWW;
-    const int q4 = cw & 3, kh = cw >> 2;
+  } else if (warp < L2_ROWW + 4) {
+    // ============================== A warps (4): A_hat block -> TMEM ==============================
+    // thread = tile row; one 16-column K chunk = two 8-column blocks; chunks go two at a time so that ONE tcgen05.wait::st
+    // covers four stores.  Chunk c of the NEXT tile may be written as soon as this tile's phase B has consumed T chunk c.
+    const int q4 = warp & 3, atid = tid - 32 * L2_ROWW;
     const int row = q4 * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
-    const int gt = ctid & 127;
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+      const Tile tl = tile_of(p, t);
+      const int L = tl.L, m = tl.m;
+      const int nchA = (L + 15) >> 4, k8n = (L + 7) >> 3;
+      const float* A = p.adj_blk + p.blk_off[tl.b] + (i64)m * L * L;
+      const int leadw = (int)((reinterpret_cast<uintptr_t>(A) & 15) >> 2);
+      const float* arow = araw + leadw + row * L;
+      const bool vec = (leadw == 0) && ((L & 3) == 0);
+      L2_STAMP(atid == 0, 12);
+      umma::mbar_wait(&bars[BAR_ARAW_FULL], (uint32_t)(it & 1));
+      L2_STAMP(atid == 0, 13);
+#pragma unroll 1
+      for (int c2 = 0; c2 < nchA; c2 += 2) {
+        const int cend = min(c2 + 2, nchA);
+        if (it > 0) {
+          for (int c = c2; c < cend; c++)
+            if (c < L2_WCHUNKS) umma::mbar_wait(&bars[BAR_T_USED + c], (uint32_t)((it - 1) & 1));
+          umma::tc_fence_after_sync();
+        }
+        if (c2 == 0) L2_STAMP(atid == 0, 14);
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          const int j8 = 2 * c2 + jj;
+          if (j8 < k8n) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[e] = 0.f;
+            if (row < L) {
+              const int k = 8 * j8;
+              if (vec) {
+                if (k < L) {
+                  const float4 a = *reinterpret_cast<const float4*>(arow + k);
+                  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                }
+                if (k + 4 < L) {
+                  const float4 a = *reinterpret_cast<const float4*>(arow + k + 4);
+                  v[4] = a.x; v[5] = a.y; v[6] = a.z; v[7] = a.w;
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; e++)
+                  if (k + e < L) v[e] = arow[k + e];
+              }
+            }
+            split_st8(tlane, (uint32_t)(8 * j8), v);
+          }
+        }
+        tmem_wait_st();
+        umma::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0)
+          for (int c = c2; c < cend; c++) mbar_arrive(&bars[BAR_A_RDY + c]);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        for (int c = nchA; c < 8; c++) mbar_arrive(&bars[BAR_A_RDY + c]);      // every barrier completes once per tile (parity = tile index)
+        mbar_arrive(&bars[BAR_ARAW_FREE]);
+      }
+      L2_STAMP(atid == 0, 15);
+    }
+  } else if (warp < L2_ROWW + L2_CONVW) {
+    // ============================== z warps (4): z block -> B operand of phase A ==============================
+    // B(n = feature, k = block row) = z[k][n].  A thread loads a 4 x 4 block (rows k..k+3, columns 4 cg..4 cg+3) with four
+    // coalesced 128-bit loads (two chunks ahead), transposes it in registers and stores four hi and four lo pieces.
+    const int gt = tid - 32 * (L2_ROWW + 4);
     const int zkq = gt / 28, zcg = gt - 28 * zkq;              // gt < 112: block (column group zcg, k-quad zkq)
     const bool zact = gt < 112, zcol = zact && zcg < 25;
     const int zo = (zcg >> 1) * L2_SBO + zkq * L2_LBO + (zcg & 1) * 64;
@@ -362,7 +441,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) gcn_layer2_kernel(GcnLayerArgs 
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
       const Tile tl = tile_of(p, t);
       const int L = tl.L, m = tl.m;
-      const int nchA = (L + 15) >> 4, k8n = (L + 7) >> 3;
+      const int nchA = (L + 15) >> 4;
       const float* zp = p.zin + ((i64)m * p.N + tl.off + 4 * zkq) * p.ldz + 4 * zcg;
       float4 zr[2][4];
       auto load_z = [&](int c, float4 (&d)[4]) {
@@ -372,96 +451,45 @@ __global__ void __launch_bounds__(L2_THREADS, 1) gcn_layer2_kernel(GcnLayerArgs 
         for (int j = 0; j < 4; j++)
           d[j] = (zcol && k0 + j < L) ? __ldg(reinterpret_cast<const float4*>(q + (i64)j * p.ldz)) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
-      // this group's chunks: c = kh, kh + 2, ...; two of them in flight
-      if (kh < nchA) load_z(kh, zr[0]);
-      if (kh + 2 < nchA) load_z(kh + 2, zr[1]);
-      const float* A = p.adj_blk + p.blk_off[tl.b] + (i64)m * L * L;
-      const int leadw = (int)((reinterpret_cast<uintptr_t>(A) & 15) >> 2);
-      const float* arow = araw + leadw + row * L;
-      const bool vec = (leadw == 0) && ((L & 3) == 0);
-      L2_STAMP(ctid == 0, 12);
-      umma::mbar_wait(&bars[BAR_ARAW_FULL], (uint32_t)(it & 1));
-      L2_STAMP(ctid == 0, 13);
+      load_z(0, zr[0]);
+      if (1 < nchA) load_z(1, zr[1]);
 #pragma unroll 1
-      for (int c4 = 0; c4 < nchA; c4 += 4) {
+      for (int c2 = 0; c2 < nchA; c2 += 2) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int c = c4 + u;
+        for (int u = 0; u < 2; u++) {
+          const int c = c2 + u;
           if (c < nchA) {
-            // ---- (a) A_hat chunk c
-            if (it > 0 && c < L2_WCHUNKS) {
-              umma::mbar_wait(&bars[BAR_T_USED + c], (uint32_t)((it - 1) & 1));
-              umma::tc_fence_after_sync();
-            }
-            if (c == 0) L2_STAMP(ctid == 0, 14);
-            const int j8 = 2 * c + kh;
-            if (j8 < k8n) {
-              float v[8];
+            float4 h[4], l[4];
 #pragma unroll
-              for (int e = 0; e < 8; e++) v[e] = 0.f;
-              if (row < L) {
-                const int k = 8 * j8;
-                if (vec) {
-                  if (k < L) {
-                    const float4 a = *reinterpret_cast<const float4*>(arow + k);
-                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-                  }
-                  if (k + 4 < L) {
-                    const float4 a = *reinterpret_cast<const float4*>(arow + k + 4);
-                    v[4] = a.x; v[5] = a.y; v[6] = a.z; v[7] = a.w;
-                  }
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 8; e++)
-                    if (k + e < L) v[e] = arow[k + e];
-                }
-              }
-              split_st8(tlane, (uint32_t)(8 * j8), v);
-              tmem_wait_st();
+            for (int i = 0; i < 4; i++) {
+              const float a0 = i == 0 ? zr[u][0].x : i == 1 ? zr[u][0].y : i == 2 ? zr[u][0].z : zr[u][0].w;
+              const float a1 = i == 0 ? zr[u][1].x : i == 1 ? zr[u][1].y : i == 2 ? zr[u][1].z : zr[u][1].w;
+              const float a2 = i == 0 ? zr[u][2].x : i == 1 ? zr[u][2].y : i == 2 ? zr[u][2].z : zr[u][2].w;
+              const float a3 = i == 0 ? zr[u][3].x : i == 1 ? zr[u][3].y : i == 2 ? zr[u][3].z : zr[u][3].w;
+              gl_split(a0, h[i].x, l[i].x);
+              gl_split(a1, h[i].y, l[i].y);
+              gl_split(a2, h[i].z, l[i].z);
+              gl_split(a3, h[i].w, l[i].w);
             }
-            umma::tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[BAR_A_RDY + c]);
-            // ---- (b) z chunk c (this group's turn when (c & 1) == kh)
-            if ((c & 1) == kh) {
-              const int slot = (u >> 1) & 1;                      // c4 is a multiple of 4: compile-time register slot
-              float4 h[4], l[4];
+            if (c + 2 < nchA) load_z(c + 2, zr[u]);
+            const uint32_t g = gc + (uint32_t)c;
+            const int s = (int)(g % (uint32_t)ns);
+            if (g >= (uint32_t)ns) umma::mbar_wait(&bars[BAR_FREE + s], ((g / (uint32_t)ns) - 1u) & 1u);
+            if (zact) {
+              uint8_t* st = ring + s * L2_STAGE + zo;
 #pragma unroll
               for (int i = 0; i < 4; i++) {
-                const float a0 = i == 0 ? zr[slot][0].x : i == 1 ? zr[slot][0].y : i == 2 ? zr[slot][0].z : zr[slot][0].w;
-                const float a1 = i == 0 ? zr[slot][1].x : i == 1 ? zr[slot][1].y : i == 2 ? zr[slot][1].z : zr[slot][1].w;
-                const float a2 = i == 0 ? zr[slot][2].x : i == 1 ? zr[slot][2].y : i == 2 ? zr[slot][2].z : zr[slot][2].w;
-                const float a3 = i == 0 ? zr[slot][3].x : i == 1 ? zr[slot][3].y : i == 2 ? zr[slot][3].z : zr[slot][3].w;
-                gl_split(a0, h[i].x, l[i].x);
-                gl_split(a1, h[i].y, l[i].y);
-                gl_split(a2, h[i].z, l[i].z);
-                gl_split(a3, h[i].w, l[i].w);
+                *reinterpret_cast<float4*>(st + 16 * i) = h[i];
+                *reinterpret_cast<float4*>(st + L2_BPART + 16 * i) = l[i];
               }
-              if (c + 4 < nchA) load_z(c + 4, zr[slot]);
-              const uint32_t g = gc + (uint32_t)c;
-              const int s = (int)(g % (uint32_t)ns);
-              if (g >= (uint32_t)ns) umma::mbar_wait(&bars[BAR_FREE + s], ((g / (uint32_t)ns) - 1u) & 1u);
-              if (zact) {
-                uint8_t* st = ring + s * L2_STAGE + zo;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                  *reinterpret_cast<float4*>(st + 16 * i) = h[i];
-                  *reinterpret_cast<float4*>(st + L2_BPART + 16 * i) = l[i];
-                }
-              }
-              umma::fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&bars[BAR_FULL + s]);
             }
+            umma::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[BAR_FULL + s]);
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) {
-        for (int c = nchA; c < 8; c++) mbar_arrive(&bars[BAR_A_RDY + c]);      // every barrier completes once per tile (parity = tile index)
-        mbar_arrive(&bars[BAR_ARAW_FREE]);
-      }
-      L2_STAMP(ctid == 0, 16);
+      L2_STAMP(gt == 0, 16);
       gc += (uint32_t)(nchA + L2_WCHUNKS);
     }
   } else if (warp == L2_W_MMA) {
@@ -493,14 +521,15 @@ __global__ void __launch_bounds__(L2_THREADS, 1) gcn_layer2_kernel(GcnLayerArgs 
           const int nch = ph == 0 ? nchA : L2_WCHUNKS, ks = ph == 0 ? ksA : 13;
           uint32_t s = gc % (uint32_t)ns, par = (gc / (uint32_t)ns) & 1u;
           if (ph == 1) umma::mbar_wait(&bars[BAR_T_DRAINED], tpar);                     // the hop has read T out of the accumulators
-          for (int c = 0; c < nch; c++) {
+          for (int i = 0; i < nch; i++) {
+            const int c = ph == 0 ? i : l2_bchunk(i);
             umma::mbar_wait(&bars[(ph == 0 ? BAR_A_RDY : BAR_T_RDY) + c], tpar);       // A operand chunk c is in TMEM
             umma::mbar_wait(&bars[BAR_FULL + s], par);
             umma::tc_fence_after_sync();
-            if (c == 0) L2_STAMP(lane == 0, ph == 0 ? 20 : 23);
-            if (c == nch - 1) L2_STAMP(lane == 0, ph == 0 ? 21 : 24);
+            if (i == 0) L2_STAMP(lane == 0, ph == 0 ? 20 : 23);
+            if (i == nch - 1) L2_STAMP(lane == 0, ph == 0 ? 21 : 24);
             const uint32_t dlo = d0_lo + s * (L2_STAGE >> 4);
-            kstep(dlo, (uint32_t)(16 * c), c > 0 ? 1u : 0u);
+            kstep(dlo, (uint32_t)(16 * c), i > 0 ? 1u : 0u);
             if (ks - 2 * c > 1) kstep(dlo + ((2 * L2_LBO) >> 4), (uint32_t)(16 * c + 8), 1u);
             umma::mma_commit_elect(&bars[BAR_FREE + s]);
             if (ph == 1) umma::mma_commit_elect(&bars[BAR_T_USED + c]);
@@ -547,16 +576,33 @@ __global__ void __launch_bounds__(L2_THREADS, 1) gcn_layer2_kernel(GcnLayerArgs 
         for (int r = lane; r < L; r += 32) bulk_g2s(dst + r * L2_G, src + (i64)r * ld, 400u, bar);
       }
     };
+    // L rows of the X buffer -> dst (row stride ld); returns when the copy engine has READ the buffer
+    auto store_rows = [&](float* dst, i64 ld, int L) {
+      if (ld == L2_G) {
+        if (lane == 0) bulk_s2g(dst, X, 400u * (uint32_t)L);
+      } else {
+        for (int r = lane; r < L; r += 32) bulk_s2g(dst + (i64)r * ld, X + r * L2_G, 400u);
+      }
+      bulk_commit_wait_read();
+      __syncwarp();
+    };
     uint32_t xyw = 0;
     int it = 0;
+    i64 prev_row0 = 0;
+    int prev_L = 0;
     if ((int)blockIdx.x < ntiles) issue_araw(blockIdx.x);
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
       const Tile tl = tile_of(p, t);
       const int L = tl.L, m = tl.m;
       const i64 row0 = (i64)m * p.N + tl.off;
       const int o1 = (m == 0) ? 1 : 0, o2 = (m == 2) ? 1 : 2;
-      // cross-modal rows of the hop
-      if (it > 0) { umma::mbar_wait(&bars[BAR_XY_FREE], xyw & 1); xyw++; }
+      // the previous tile's result rows leave from X; then the cross-modal rows of this tile's hop arrive
+      if (it > 0) {
+        umma::mbar_wait(&bars[BAR_XY_FREE], xyw & 1);
+        xyw++;
+        if (FWD && lane == 0 && mask_by_tma(p, prev_row0, prev_L)) bulk_s2g(p.flags + prev_row0 * L2_G, mask_s, 100u * (uint32_t)prev_L);
+        store_rows(p.out + prev_row0 * p.ldo, p.ldo, prev_L);
+      }
       issue_rows(X, p.zin + ((i64)o1 * p.N + tl.off) * p.ldz, p.ldz, L, &bars[BAR_X_FULL]);
       issue_rows(Y, p.zin + ((i64)o2 * p.N + tl.off) * p.ldz, p.ldz, L, &bars[BAR_Y_FULL]);
       // the next tile's A_hat block, as soon as the converters have read this one
@@ -564,16 +610,31 @@ __global__ void __launch_bounds__(L2_THREADS, 1) gcn_layer2_kernel(GcnLayerArgs 
         umma::mbar_wait(&bars[BAR_ARAW_FREE], (uint32_t)(it & 1));
         issue_araw(t + gridDim.x);
       }
-      // operands of the epilogue
+      // after the hop: (backward) the T rows leave from X; then the operands of the epilogue arrive
       umma::mbar_wait(&bars[BAR_XY_FREE], xyw & 1);
       xyw++;
       if (FWD) {
+        if (p.mask && mask_by_tma(p, row0, L)) {               // the keep bytes ride on the Y barrier (its own expect_tx arrival)
+          if (lane == 0) {
+            asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(umma::smem_u32(&bars[BAR_Y_FULL])), "r"(100u * (uint32_t)L) : "memory");
+            bulk_g2s(mask_s, p.mask + row0 * L2_G, 100u * (uint32_t)L, &bars[BAR_Y_FULL]);
+          }
+          __syncwarp();
+        }
         issue_rows(X, p.r + row0 * p.ldr, p.ldr, L, &bars[BAR_X_FULL]);
         issue_rows(Y, p.q ? p.q + row0 * L2_G : nullptr, L2_G, L, &bars[BAR_Y_FULL]);
       } else {
+        store_rows(p.t_out + row0 * p.ldt, p.ldt, L);
         issue_rows(X, nullptr, 0, L, &bars[BAR_X_FULL]);
         issue_rows(Y, p.add ? p.add + row0 * L2_G : nullptr, L2_G, L, &bars[BAR_Y_FULL]);
       }
+      prev_row0 = row0;
+      prev_L = L;
+    }
+    if (it > 0) {
+      umma::mbar_wait(&bars[BAR_XY_FREE], xyw & 1);
+      if (FWD && lane == 0 && mask_by_tma(p, prev_row0, prev_L)) bulk_s2g(p.flags + prev_row0 * L2_G, mask_s, 100u * (uint32_t)prev_L);
+      store_rows(p.out + prev_row0 * p.ldo, p.ldo, prev_L);
     }
     __syncwarp();
   } else {
@@ -591,7 +652,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) gcn_layer2_kernel(GcnLayerArgs 
           if (c >= nchA) {
             mbar_arrive_cnt(&bars[BAR_FULL + s], 3);
             mbar_expect_tx(&bars[BAR_FULL + s], L2_STAGE);
-            bulk_g2s(ring + s * L2_STAGE, p.wimg + (i64)(c - nchA) * (L2_STAGE / 4), L2_STAGE, &bars[BAR_FULL + s]);
+            bulk_g2s(ring + s * L2_STAGE, p.wimg + (i64)l2_bchunk(c - nchA) * (L2_STAGE / 4), L2_STAGE, &bars[BAR_FULL + s]);
           }
           gc++;
         }

@@ -140,26 +140,25 @@ __global__ void __launch_bounds__(ST_THREADS, 2) adj_spmm_tc_kernel(SpmmTcArgs p
 
   if (warp == 8) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (lane == 0)
       for (int c = 1; c < nchunks; c++) issue_z(c);           // each issue costs ~250 cycles: off the converters' path
+    __syncwarp();
+    {
+      const uint64_t d0 = umma::smem_desc(umma::smem_u32(stages), ST_LBO, ST_SBO);
+      const uint32_t dhi = (uint32_t)(d0 >> 32), dlo = (uint32_t)d0;
       for (int c = 0; c < nchunks; c++) {
         const int s = c & 1;
         umma::mbar_wait(&bar_full[s], (uint32_t)((c >> 1) & 1));
         umma::tc_fence_after_sync();
-        const uint32_t base = umma::smem_u32(stages + s * ST_STAGE);
+        const uint32_t o = dlo + (uint32_t)s * (ST_STAGE >> 4);
         const int kleft = L - c * ST_KC;
         const int ksteps = kleft >= ST_KC ? ST_KC / 8 : (kleft + 7) / 8;
         for (int j = 0; j < ksteps; j++) {
-          const uint64_t a_hi = umma::smem_desc(base + j * 2 * ST_LBO, ST_LBO, ST_SBO);
-          const uint64_t a_lo = umma::smem_desc(base + ST_A_PART + j * 2 * ST_LBO, ST_LBO, ST_SBO);
-          const uint64_t b_hi = umma::smem_desc(base + 2 * ST_A_PART + j * 2 * ST_LBO, ST_LBO, ST_SBO);
-          const uint64_t b_lo = umma::smem_desc(base + 2 * ST_A_PART + ST_B_PART + j * 2 * ST_LBO, ST_LBO, ST_SBO);
-          const uint32_t first = (c > 0 || j > 0) ? 1u : 0u;
-          umma::mma_tf32(tmem, a_hi, b_hi, IDESC, first);
-          umma::mma_tf32(tmem + ST_CORR, a_lo, b_hi, IDESC, first);
-          umma::mma_tf32(tmem + ST_CORR, a_hi, b_lo, IDESC, 1u);
+          const uint32_t oj = o + (uint32_t)j * ((2 * ST_LBO) >> 4);
+          umma::kstep3_elect(tmem, tmem + ST_CORR, dhi, oj, oj + (ST_A_PART >> 4), oj + ((2 * ST_A_PART) >> 4),
+                             oj + ((2 * ST_A_PART + ST_B_PART) >> 4), IDESC, (c > 0 || j > 0) ? 1u : 0u);
         }
-        umma::mma_commit(&bar_free[s]);
+        umma::mma_commit_elect(&bar_free[s]);
       }
     }
     __syncwarp();

@@ -128,28 +128,28 @@ __global__ void __launch_bounds__(SL_THREADS, 2) adj_spmm_tc_long_kernel(SpmmLon
 
   if (warp == 8) {
     // ===== MMA issuer + z producer =====
-    if (lane == 0) {
+    if (lane == 0)
       for (int c = 1; c < SL_ZR && c < nchunks; c++) issue_z(c);
+    __syncwarp();
+    {
+      const uint64_t d0 = umma::smem_desc(umma::smem_u32(stages), SL_LBO, SL_SBO);
+      const uint32_t dhi = (uint32_t)(d0 >> 32), dlo = (uint32_t)d0;
       for (int c = 0; c < nchunks; c++) {
         const int s = c & 1;
         umma::mbar_wait(&bar_full[s], (uint32_t)((c >> 1) & 1));
         umma::tc_fence_after_sync();
         // every converter has finished reading ring slot c % SL_ZR (it arrived on bar_full after its reads): refill it
-        if (c + SL_ZR < nchunks) issue_z(c + SL_ZR);
-        const uint32_t base = umma::smem_u32(stages + s * SL_STAGE);
+        if (lane == 0 && c + SL_ZR < nchunks) issue_z(c + SL_ZR);
+        __syncwarp();
+        const uint32_t o = dlo + (uint32_t)s * (SL_STAGE >> 4);
         const int kleft = L - c * SL_KC;
         const int ksteps = kleft >= SL_KC ? SL_KC / 8 : (kleft + 7) / 8;
         for (int j = 0; j < ksteps; j++) {
-          const uint64_t a_hi = umma::smem_desc(base + j * 2 * SL_LBO, SL_LBO, SL_SBO);
-          const uint64_t a_lo = umma::smem_desc(base + SL_A_PART + j * 2 * SL_LBO, SL_LBO, SL_SBO);
-          const uint64_t b_hi = umma::smem_desc(base + 2 * SL_A_PART + j * 2 * SL_LBO, SL_LBO, SL_SBO);
-          const uint64_t b_lo = umma::smem_desc(base + 2 * SL_A_PART + SL_B_PART + j * 2 * SL_LBO, SL_LBO, SL_SBO);
-          const uint32_t first = (c > 0 || j > 0) ? 1u : 0u;
-          umma::mma_tf32(tmem, a_hi, b_hi, IDESC, first);
-          umma::mma_tf32(tmem + SL_CORR, a_lo, b_hi, IDESC, first);
-          umma::mma_tf32(tmem + SL_CORR, a_hi, b_lo, IDESC, 1u);
+          const uint32_t oj = o + (uint32_t)j * ((2 * SL_LBO) >> 4);
+          umma::kstep3_elect(tmem, tmem + SL_CORR, dhi, oj, oj + (SL_A_PART >> 4), oj + ((2 * SL_A_PART) >> 4),
+                             oj + ((2 * SL_A_PART + SL_B_PART) >> 4), IDESC, (c > 0 || j > 0) ? 1u : 0u);
         }
-        umma::mma_commit(&bar_free[s]);
+        umma::mma_commit_elect(&bar_free[s]);
       }
     }
     __syncwarp();

@@ -155,6 +155,27 @@ __device__ __forceinline__ void mma_tf32_elect(uint32_t tmem_d, uint64_t adesc, 
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One k-step of the 3-term tf32 split (main += a_hi b_hi; corr += a_lo b_hi; corr += a_hi b_lo) from shared-memory
+// operands, issued by one elected lane of a converged warp.  dhi = high word shared by all four descriptors, the other
+// four arguments are their low words (start-address field: base + byte offset / 16).
+__device__ __forceinline__ void kstep3_elect(uint32_t tmem_main, uint32_t tmem_corr, uint32_t dhi, uint32_t a_hi, uint32_t a_lo,
+                                             uint32_t b_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e, t;\n\t.reg .b64 ah, al, bh, bl;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %8, 0;\n\t"
+      "setp.eq.b32 t, %8, %8;\n\t"
+      "mov.b64 ah, {%3, %2};\n\t"
+      "mov.b64 al, {%4, %2};\n\t"
+      "mov.b64 bh, {%5, %2};\n\t"
+      "mov.b64 bl, {%6, %2};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %7, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %7, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bl, %7, t;\n\t}"
+      ::"r"(tmem_main), "r"(tmem_corr), "r"(dhi), "r"(a_hi), "r"(a_lo), "r"(b_hi), "r"(b_lo), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred e;\n\t"

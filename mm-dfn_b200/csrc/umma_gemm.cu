@@ -229,27 +229,27 @@ __global__ void __launch_bounds__(UG_ALL_THREADS, BN <= 128 ? 2 : 1) umma_gemm_k
 
   if (warp == 8) {
     // ===== MMA issuer: one thread feeds the tensor core as soon as a stage is full; it never touches operand data =====
-    if (lane == 0) {
+    // The whole warp runs the loop convergently and one elected lane issues (umma::kstep3_elect): from inside a lane-0
+    // branch every MMA cost ~117 cycles of the issuing thread (R2UR / ELECT sequences, descriptors rebuilt per
+    // instruction) against 54 of tensor time (tools/umma_rate.py).
+    {
+      const uint64_t d0 = umma::smem_desc(umma::smem_u32(smem), UG_LBO, UG_SBO);
+      const uint32_t dhi = (uint32_t)(d0 >> 32), dlo = (uint32_t)d0;
       for (int c = 0; c < nchunks; c++) {
         const int s = c % UG_STAGES;
         umma::mbar_wait(&bar_full[s], (uint32_t)((c / UG_STAGES) & 1));
         umma::tc_fence_after_sync();
-        const uint32_t base = umma::smem_u32(smem + s * UG_STAGE_BYTES);
+        const uint32_t o = dlo + (uint32_t)s * (UG_STAGE_BYTES >> 4);
         const int kleft = ke - (kb + c * UG_KC);
         const int ksteps = kleft >= UG_KC ? UG_KC / 8 : (kleft + 7) / 8;
+        // the large hi*hi term and the 2^-11-scaled corrections accumulate in separate TMEM tiles, so the tensor
+        // core's truncating fp32 accumulate touches the main sum once per k-step instead of three times
         for (int j = 0; j < ksteps; j++) {
-          const uint64_t a_hi = umma::smem_desc(base + j * 2 * UG_LBO, UG_LBO, UG_SBO);
-          const uint64_t a_lo = umma::smem_desc(base + UG_A_PART + j * 2 * UG_LBO, UG_LBO, UG_SBO);
-          const uint64_t b_hi = umma::smem_desc(base + 2 * UG_A_PART + j * 2 * UG_LBO, UG_LBO, UG_SBO);
-          const uint64_t b_lo = umma::smem_desc(base + 2 * UG_A_PART + UG_B_PART + j * 2 * UG_LBO, UG_LBO, UG_SBO);
-          const uint32_t first = (c > 0 || j > 0) ? 1u : 0u;
-          // the large hi*hi term and the 2^-11-scaled corrections accumulate in separate TMEM tiles, so the tensor
-          // core's truncating fp32 accumulate touches the main sum once per k-step instead of three times
-          umma::mma_tf32(tmem, a_hi, b_hi, IDESC, first);
-          umma::mma_tf32(tmem + UG_CORR_COL, a_lo, b_hi, IDESC, first);
-          umma::mma_tf32(tmem + UG_CORR_COL, a_hi, b_lo, IDESC, 1u);
+          const uint32_t oj = o + (uint32_t)j * ((2 * UG_LBO) >> 4);
+          umma::kstep3_elect(tmem, tmem + UG_CORR_COL, dhi, oj, oj + (UG_A_PART >> 4), oj + ((2 * UG_A_PART) >> 4),
+                             oj + ((2 * UG_A_PART + UG_B_PART) >> 4), IDESC, (c > 0 || j > 0) ? 1u : 0u);
         }
-        umma::mma_commit(&bar_free[s]);
+        umma::mma_commit_elect(&bar_free[s]);
       }
     }
     umma::tc_fence_before_sync();

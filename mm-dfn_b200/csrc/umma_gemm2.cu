@@ -173,31 +173,22 @@ __global__ void __launch_bounds__(G2_THREADS, 2) umma_gemm2_kernel(G2Args p) {
     // ===== MMA issuer (lane 0) + raw-chunk producer (all lanes) =====
     if (!A_KMAJ || !B_KMAJ)
       for (int c = 0; c < RING && c < nchunks; c++) issue_raw(c, lane);
+    const uint64_t d0 = umma::smem_desc(umma::smem_u32(stages), G2_LBO, G2_SBO);
+    const uint32_t dhi = (uint32_t)(d0 >> 32), dlo = (uint32_t)d0;
     for (int c = 0; c < nchunks; c++) {
       const int s = c % G2_NS;
-      if (lane == 0) {
-        umma::mbar_wait(&bar_full[s], (uint32_t)((c / G2_NS) & 1));
-        umma::tc_fence_after_sync();
-      }
-      __syncwarp();
+      umma::mbar_wait(&bar_full[s], (uint32_t)((c / G2_NS) & 1));       // the whole warp: the MMA issue below is convergent
+      umma::tc_fence_after_sync();
       if ((!A_KMAJ || !B_KMAJ) && c + RING < nchunks) issue_raw(c + RING, lane);      // slot c % RING was fully read
-      if (lane == 0) {
-        const uint32_t base = umma::smem_u32(stages + s * G2_STAGE);
-        const int kleft = ke - (kb + c * G2_KC);
-        const int ksteps = kleft >= G2_KC ? G2_KC / 8 : (kleft + 7) / 8;
-        for (int j = 0; j < ksteps; j++) {
-          const uint64_t a_hi = umma::smem_desc(base + j * 2 * G2_LBO, G2_LBO, G2_SBO);
-          const uint64_t a_lo = umma::smem_desc(base + G2_A_PART + j * 2 * G2_LBO, G2_LBO, G2_SBO);
-          const uint64_t b_hi = umma::smem_desc(base + 2 * G2_A_PART + j * 2 * G2_LBO, G2_LBO, G2_SBO);
-          const uint64_t b_lo = umma::smem_desc(base + 2 * G2_A_PART + G2_B_PART + j * 2 * G2_LBO, G2_LBO, G2_SBO);
-          const uint32_t acc = (c > 0 || j > 0) ? 1u : 0u;
-          umma::mma_tf32(tmem, a_hi, b_hi, IDESC, acc);
-          umma::mma_tf32(tmem + G2_CORR, a_lo, b_hi, IDESC, acc);
-          umma::mma_tf32(tmem + G2_CORR, a_hi, b_lo, IDESC, 1u);
-        }
-        umma::mma_commit(&bar_free[s]);
+      const uint32_t o = dlo + (uint32_t)s * (G2_STAGE >> 4);
+      const int kleft = ke - (kb + c * G2_KC);
+      const int ksteps = kleft >= G2_KC ? G2_KC / 8 : (kleft + 7) / 8;
+      for (int j = 0; j < ksteps; j++) {
+        const uint32_t oj = o + (uint32_t)j * ((2 * G2_LBO) >> 4);
+        umma::kstep3_elect(tmem, tmem + G2_CORR, dhi, oj, oj + (G2_A_PART >> 4), oj + ((2 * G2_A_PART) >> 4),
+                           oj + ((2 * G2_A_PART + G2_B_PART) >> 4), IDESC, (c > 0 || j > 0) ? 1u : 0u);
       }
-      __syncwarp();
+      umma::mma_commit_elect(&bar_free[s]);
     }
     umma::tc_fence_before_sync();
     __syncthreads();
