@@ -43,7 +43,7 @@ N_BATCHES = 8                      # distinct input batches rotated so that step
 CPU_SAMPLE_DIALOGUES = 8
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE gcn_layer_kernel<fwd> launch inside a training step of the default
 # workload, read from the committed `ncu --set full` capture (profiles/, see profiles/README.md); None = not captured yet
-NCU_TRAFFIC_BYTES = 17593088          # profiles/r02_ncu_gcn_layer_and_gemm2.csv: 17.59 MB read + 0 written (outputs stay in L2)
+NCU_TRAFFIC_BYTES = 17627648          # profiles/r02_ncu_gcn_layer2.csv: 17.63 MB read + 0 written (outputs stay in L2)
 METRIC = "utterances/sec (fwd+bwd) IEMOCAP-shape"
 UNIT = "utterances/s"
 
@@ -392,8 +392,9 @@ def roofline_graph_conv(dev, n_dialogues=DIALOGUES_PER_GPU):
     us_copy, _ = timed_us(launch_copy)
     peak, how = measured_peak_gbs()
     achieved = alg_bytes / (us * 1e-6) / 1e9
-    return {"kernel": "gcn_layer_kernel<fwd> (fused GraphConvolution layer: tcgen05 3xTF32 aggregate hi = A_hat z chained with hi Mtop, "
-                      "+ h0 term, ReLU, dropout, + q in one launch; fp32-level accuracy)", "bound": "hbm",
+    return {"kernel": "gcn_layer2_kernel<fwd> (fused GraphConvolution layer, persistent CTA per SM: tcgen05 3xTF32 aggregate hi = A_hat z with "
+                      "A operands in tensor memory, chained with hi Mtop, + h0 term, ReLU, dropout, + q in one launch; fp32-level accuracy)",
+            "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel inside a training step, from the
             # committed `ncu --set full` capture (profiles/README.md names the file); null until that capture exists
