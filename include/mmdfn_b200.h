@@ -214,6 +214,29 @@ int mmdfn_focal_loss_bwd(int N, int C, const float* log_prob, const long long* t
 int mmdfn_confusion_accumulate(int N, int C, const float* log_prob, const long long* target, long long* pred,
                                unsigned long long* conf, void* stream);
 
+/* ---- a13 (star row): Memory Fusion Network block -- MFN.forward (code/model_fusion.py:62-120) and its backward --------
+ * x (T, n, 900) = [l | a | v] -> out (T, n, 400) = [h_l | h_a | h_v | mem].  params: the first 28 tensors of the module's
+ * state_dict in order (lstm_{l,a,v}.{weight_ih, weight_hh, bias_ih, bias_hh}, att1_fc1/2, att2_fc1/2, gamma1_fc1/2,
+ * gamma2_fc1/2: weight, bias; out_fc1 / out_fc2 are constructed by the reference but never used).  masks: NULL (eval) or
+ * 4 uint8 keep masks (T n, 100) for the block's four Dropout(0.2) layers (after att1_fc1, att2_fc1, gamma1_fc1,
+ * gamma2_fc1), mask_scale = 1 / (1 - 0.2).  ws: mmdfn_mfn_ws_floats floats, kept for the backward.  dparams receive "=". */
+long long mmdfn_mfn_ws_floats(int T, int n);
+long long mmdfn_mfn_bwd_ws_floats(int T, int n);
+int mmdfn_mfn_fwd(int T, int n, const float* x, const float* const* params, const unsigned char* const* masks,
+                  float mask_scale, float* out, float* ws, void* stream);
+int mmdfn_mfn_bwd(int T, int n, const float* x, const float* const* params, const unsigned char* const* masks,
+                  float mask_scale, const float* out, const float* ws_fwd, const float* dout, float* dx,
+                  float* const* dparams, float* ws, void* stream);
+/* glue of the 'mfn' head (code/model.py:1263-1291, 1303-1330): stacked node features F (3N, 300) -> padded time-major
+ * window x (T, B, 900) with x[.., 300 j ..] taken from modality block p_j; MFN output (T, B, 400) -> node rows (N, 400);
+ * y = relu(x) * keep * scale (Dropout then ReLU) and its backward dx = y != 0 ? dy * ind_scale : 0. */
+int mmdfn_mfn_pack_fwd(int T, int B, int N, const int* dia_off, int p0, int p1, int p2, const float* F, float* x, void* stream);
+int mmdfn_mfn_pack_bwd(int T, int B, int N, const int* dia_off, int p0, int p1, int p2, const float* dx, float* dF, void* stream);
+int mmdfn_mfn_unpad_fwd(int T, int B, const int* dia_off, const float* out, float* feat, void* stream);
+int mmdfn_mfn_unpad_bwd(int T, int B, const int* dia_off, const float* dfeat, float* dout, void* stream);
+int mmdfn_relu_mask_fwd(long long n, const float* x, const unsigned char* mask, float scale, float* y, void* stream);
+int mmdfn_relu_mask_bwd(long long n, const float* dy, const float* y, float ind_scale, float* dx, void* stream);
+
 /* ---- k10/k11 (relation graph type): edges and masked edge attention ----------------------------
  * edge_perms + batch_graphify (code/model.py:532-550, 568-611) and MaskedEdgeAttention 'attn1' (:449-471).
  * Canonical edge order: dialogue, source j, target i ascending; edge_off (B+1) int64 = per-dialogue edge

@@ -318,6 +318,64 @@ def simple_batch_graphify(features, lengths, no_cuda):
 # ------------------------------------------------------------------------------------------------
 # code/model.py:784-1407
 # ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------
+# code/model_fusion.py:10-120
+# ------------------------------------------------------------------------------------------------
+class MFN(nn.Module):
+    """Memory Fusion Network block (Zadeh et al., AAAI 2018) as the reference builds it (code/model_fusion.py:14-60): same
+    sub-modules in the same order (identical state_dict keys and seed-for-seed initial weights); forward(x) with
+    x (T, n, 3 d) -> (T, n, 400) runs on the CUDA path (mmdfn_mfn_fwd / _bwd).  `masks` (tests only): four uint8 keep
+    masks (T n, 100) for the Dropout(0.2) layers after att1_fc1, att2_fc1, gamma1_fc1, gamma2_fc1."""
+
+    def __init__(self, d=300, config=None):
+        super().__init__()
+        if d != 300:
+            raise NotImplementedError("MFN: the CUDA path is built for d = 300 per modality (the only value the reference uses)")
+        self.d_l, self.d_a, self.d_v = d, d, d
+        self.dh_l, self.dh_a, self.dh_v = 100, 100, 100
+        total_h_dim = self.dh_l + self.dh_a + self.dh_v
+        self.mem_dim = 100
+        window_dim = 2
+        attInShape = total_h_dim * window_dim
+        gammaInShape = attInShape + self.mem_dim
+        final_out = total_h_dim + self.mem_dim
+        h = 100
+        self.drop_p = 0.2
+        self.lstm_l = nn.LSTMCell(self.d_l, self.dh_l)
+        self.lstm_a = nn.LSTMCell(self.d_a, self.dh_a)
+        self.lstm_v = nn.LSTMCell(self.d_v, self.dh_v)
+        self.att1_fc1 = nn.Linear(attInShape, h)
+        self.att1_fc2 = nn.Linear(h, attInShape)
+        self.att1_dropout = nn.Dropout(self.drop_p)
+        self.att2_fc1 = nn.Linear(attInShape, h)
+        self.att2_fc2 = nn.Linear(h, self.mem_dim)
+        self.att2_dropout = nn.Dropout(self.drop_p)
+        self.gamma1_fc1 = nn.Linear(gammaInShape, h)
+        self.gamma1_fc2 = nn.Linear(h, self.mem_dim)
+        self.gamma1_dropout = nn.Dropout(self.drop_p)
+        self.gamma2_fc1 = nn.Linear(gammaInShape, h)
+        self.gamma2_fc2 = nn.Linear(h, self.mem_dim)
+        self.gamma2_dropout = nn.Dropout(self.drop_p)
+        self.out_fc1 = nn.Linear(final_out, h)          # constructed, never used (as in the reference)
+        self.out_fc2 = nn.Linear(h, 1)
+        self.out_dropout = nn.Dropout(self.drop_p)
+
+    def _weights(self):
+        sd = dict(self.named_parameters())
+        return [sd[k] for k in ops.MFN_KEYS]
+
+    def forward(self, x, masks=None):
+        if not x.is_cuda:
+            raise ops.MMDFNError("MFN.forward needs CUDA tensors: the B200 path has no CPU fallback")
+        T, n = x.shape[0], x.shape[1]
+        scale = 1.0
+        if masks is None and self.training and self.drop_p > 0:
+            masks = ops.make_masks([(T * n, 100)] * 4, self.drop_p, x.device)
+        if masks is not None:
+            scale = 1.0 / (1.0 - self.drop_p)
+        return ops.MFNFn.apply(x, masks, scale, *self._weights())
+
+
 class DialogueGNNModel(nn.Module):
     def __init__(self, base_model, D_m, D_g, D_p, D_e, D_h, D_a, graph_hidden_size, n_speakers, max_seq_len,
                  window_past, window_future, n_classes=7, listener_state=False, context_attention='simple',
@@ -329,11 +387,11 @@ class DialogueGNNModel(nn.Module):
         super().__init__()
         if base_model != 'LSTM' or not multi_modal or sorted(modals) != ['a', 'l', 'v'] \
                 or graph_type not in ('GDF', 'relation') or av_using_lstm \
-                or not (att_type == 'concat_subsequently' or (att_type == 'gated' and graph_type == 'relation')) \
+                or not (att_type in ('concat_subsequently', 'mfn') or (att_type == 'gated' and graph_type == 'relation')) \
                 or D_e != 100 or graph_hidden_size != 100 or not use_residue or (graph_type == 'relation' and use_GCN):
             raise NotImplementedError(
                 "mmdfn_b200 implements the MM-DFN hot path only: base_model='LSTM', multi_modal, modals='avl', "
-                "graph_type='GDF' (or 'relation'), att_type='concat_subsequently' (or 'gated' with graph_type='relation'), "
+                "graph_type='GDF' (or 'relation'), att_type='concat_subsequently' or 'mfn' (or 'gated' with graph_type='relation'), "
                 "D_e=graph_hidden_size=100, use_residue")
         self.base_model, self.avec, self.no_cuda, self.graph_type = base_model, avec, no_cuda, graph_type
         self.alpha, self.lamda, self.multiheads, self.graph_construct = alpha, lamda, multiheads, graph_construct
@@ -384,8 +442,13 @@ class DialogueGNNModel(nn.Module):
                 self.edge_type_mapping[str(j) + str(k) + '1'] = len(self.edge_type_mapping)
         self.gatedatt = MMGatedAttention(2 * D_e + graph_hidden_size, graph_hidden_size, att_type='general')
         self.dropout_ = nn.Dropout(self.dropout)
-        # code/model.py:984-990: the gated fusion feeds 100 features per modality pair into the classifier
-        self.smax_fc = nn.Linear((100 if att_type == 'gated' else 300) * len(self.modals), n_classes)
+        # code/model.py:984-994: the gated fusion feeds 100 features per modality pair into the classifier, the memory
+        # fusion network 3 x 100 hidden states + the 100-d memory
+        if att_type == 'mfn':
+            self.mfn = MFN()
+            self.smax_fc = nn.Linear(400, n_classes)
+        else:
+            self.smax_fc = nn.Linear((100 if att_type == 'gated' else 300) * len(self.modals), n_classes)
 
     def _gru_weights(self, gru):
         return [getattr(gru, k) for k in ops.GRU_KEYS]
@@ -455,9 +518,25 @@ class DialogueGNNModel(nn.Module):
         if pool_gcn:
             gm = {"x": pooled[3], "h0": pooled[4], "layers": pooled[5] if len(gcn.convs) > 0 else None}
         F_ = self.graph_model.forward_stacked(X, geom, gm)
+        if self.att_type == 'mfn':
+            # code/model.py:1303-1330: emotions_feat (N, 900) = [a | v | l] blocks in that order
+            return self._mfn_head(F_, geom, T, (0, 1, 2), mk), None, None, None, None
         with ops.sink_key("head"):
             log_prob = ops.HeadFn.apply(F_, geom.N, m_h, scale, self.smax_fc.weight, self.smax_fc.bias)
         return log_prob, None, None, None, None
+
+    def _mfn_head(self, F_, geom, T, perm, mk):
+        """att_type='mfn' (code/model.py:1263-1291, 1303-1330): the node features, padded per dialogue to (T, B, 900), go
+        through the memory fusion network; its valid rows -> dropout -> ReLU -> smax_fc (400 -> C) -> log_softmax.
+        `mk` (tests only): {'mfn': four keep masks, 'mfn_head': (N, 400) keep mask}."""
+        x = ops.MFNPackFn.apply(F_, geom, T, perm)
+        feat = ops.MFNUnpadFn.apply(self.mfn(x, masks=mk.get("mfn")), geom)
+        p = float(self.dropout)
+        m_g = mk.get("mfn_head")
+        if m_g is None and self.training and p > 0 and not mk:
+            m_g = ops.make_mask((geom.N, 400), p, feat.device)
+        feat = ops.ReluMaskFn.apply(feat, m_g, 1.0 / (1.0 - p) if m_g is not None else 1.0)
+        return ops.LogSoftmaxFn.apply(ops.LinearFn.apply(feat, self.smax_fc.weight, self.smax_fc.bias))
 
     def _forward_relation(self, X, E_l, qmask, geom, seq_lengths, umask, m_h, scale, gated_masks=None):
         """graph_type='relation' (code/model.py:1182-1242): windowed speaker/temporal edges, edge weights from
@@ -487,6 +566,10 @@ class DialogueGNNModel(nn.Module):
             log_prob = ops.LogSoftmaxFn.apply(ops.LinearFn.apply(feat, self.smax_fc.weight, self.smax_fc.bias))
             return log_prob, edges.edge_index, edge_norm, edges.edge_type, list(edges.counts)
         F_ = torch.cat([self.graph_net_a(xa, *args), self.graph_net_v(xv, *args), self.graph_net_l(xl, *args)], dim=0)
+        if self.att_type == 'mfn':
+            # code/model.py:1263-1291: emotions_tmp = [emotions_l | emotions_a | emotions_v]
+            T = int(qmask.shape[0])
+            return self._mfn_head(F_, geom, T, (2, 0, 1), gated_masks or {}), edges.edge_index, edge_norm, edges.edge_type, list(edges.counts)
         log_prob = ops.HeadFn.apply(F_, N, m_h, scale, self.smax_fc.weight, self.smax_fc.bias, False)
         return log_prob, edges.edge_index, edge_norm, edges.edge_type, list(edges.counts)
 

@@ -498,6 +498,113 @@ class UnpackPadFn(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------------
+# a13: Memory Fusion Network block and the glue of the 'mfn' head
+# ---------------------------------------------------------------------------------------------
+MFN_KEYS = tuple(f"lstm_{m}.{k}" for m in "lav" for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")) + tuple(
+    f"{name}.{k}" for name in ("att1_fc1", "att1_fc2", "att2_fc1", "att2_fc2", "gamma1_fc1", "gamma1_fc2", "gamma2_fc1", "gamma2_fc2")
+    for k in ("weight", "bias"))
+
+
+def _u8_table(masks):
+    import ctypes
+    return (ctypes.c_void_p * len(masks))(*[ptr(m, U8) for m in masks])
+
+
+class MFNFn(torch.autograd.Function):
+    """MFN.forward (code/model_fusion.py:62-120): x (T, n, 900) -> (T, n, 400); masks = None or 4 uint8 keep masks (T n, 100)."""
+
+    @staticmethod
+    def forward(ctx, x, masks, mask_scale, *w):
+        x = _f32c(x)
+        w = [_f32c(t) for t in w]
+        T, n = x.shape[0], x.shape[1]
+        out = _empty((T, n, 400), x.device)
+        ws = _empty((query("mmdfn_mfn_ws_floats", T, n),), x.device)
+        tab = ptr_table(w)
+        mt = _u8_table(masks) if masks is not None else None
+        call("mmdfn_mfn_fwd", T, n, ptr(x), tab, mt, float(mask_scale), ptr(out), ptr(ws), stream())
+        ctx.save_for_backward(x, out, ws, *w)
+        ctx.masks, ctx.mask_scale = masks, float(mask_scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, out, ws, *w = ctx.saved_tensors
+        T, n = x.shape[0], x.shape[1]
+        dout = _f32c(dout)
+        dx = _empty(x.shape, x.device)
+        dw = [_empty(t.shape, x.device) for t in w]
+        wsb = _empty((query("mmdfn_mfn_bwd_ws_floats", T, n),), x.device)
+        tab, dtab = ptr_table(w), ptr_table(dw)
+        mt = _u8_table(ctx.masks) if ctx.masks is not None else None
+        call("mmdfn_mfn_bwd", T, n, ptr(x), tab, mt, ctx.mask_scale, ptr(out), ptr(ws), ptr(dout), ptr(dx), dtab, ptr(wsb), stream())
+        return (dx, None, None, *dw)
+
+
+class MFNPackFn(torch.autograd.Function):
+    """stacked node features F (3N, 300) -> padded time-major window (T, B, 900), block j from modality perm[j]."""
+
+    @staticmethod
+    def forward(ctx, F_, geom, T, perm):
+        F_ = _f32c(F_)
+        B, N = geom.B, geom.N
+        x = _empty((T, B, 900), F_.device)
+        call("mmdfn_mfn_pack_fwd", T, B, N, ptr(geom.dia_off, torch.int32), *perm, ptr(F_), ptr(x), stream())
+        ctx.geom, ctx.T, ctx.perm = geom, T, tuple(perm)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        geom = ctx.geom
+        dx = _f32c(dx)
+        dF = _empty((3 * geom.N, 300), dx.device)
+        call("mmdfn_mfn_pack_bwd", ctx.T, geom.B, geom.N, ptr(geom.dia_off, torch.int32), *ctx.perm, ptr(dx), ptr(dF), stream())
+        return dF, None, None, None
+
+
+class MFNUnpadFn(torch.autograd.Function):
+    """(T, B, 400) -> the valid rows in node order (N, 400)   (code/model.py:1280-1285)."""
+
+    @staticmethod
+    def forward(ctx, out, geom):
+        out = _f32c(out)
+        T, B = out.shape[0], out.shape[1]
+        feat = _empty((geom.N, 400), out.device)
+        call("mmdfn_mfn_unpad_fwd", T, B, ptr(geom.dia_off, torch.int32), ptr(out), ptr(feat), stream())
+        ctx.geom, ctx.shape = geom, (T, B)
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        T, B = ctx.shape
+        dfeat = _f32c(dfeat)
+        dout = _empty((T, B, 400), dfeat.device)
+        call("mmdfn_mfn_unpad_bwd", T, B, ptr(ctx.geom.dia_off, torch.int32), ptr(dfeat), ptr(dout), stream())
+        return dout, None
+
+
+class ReluMaskFn(torch.autograd.Function):
+    """y = relu(x) * keep * scale: nn.Dropout followed by nn.ReLU (code/model.py:1290-1291)."""
+
+    @staticmethod
+    def forward(ctx, x, mask, scale):
+        x = _f32c(x)
+        y = _empty(x.shape, x.device)
+        call("mmdfn_relu_mask_fwd", x.numel(), ptr(x), ptr(mask, U8), float(scale), ptr(y), stream())
+        ctx.save_for_backward(y)
+        ctx.ind = float(scale) if mask is not None else 1.0
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _f32c(dy)
+        dx = _empty(y.shape, y.device)
+        call("mmdfn_relu_mask_bwd", y.numel(), ptr(dy), ptr(y), ctx.ind, ptr(dx), stream())
+        return dx, None, None
+
+
+# ---------------------------------------------------------------------------------------------
 # k5: block-compact adjacency
 # ---------------------------------------------------------------------------------------------
 class AdjFn(torch.autograd.Function):

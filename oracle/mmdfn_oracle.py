@@ -367,7 +367,7 @@ def forward_gdf(P: Dict[str, Tensor], textf: Tensor, qmask: Tensor, lengths: Seq
                 visuf: Tensor, *, nlayers: int, speaker_weights=(1.0, 1.0, 1.0), lamda: float = 0.5,
                 alpha: float = 0.2, reason_flag: bool = True, use_crn_speaker: bool = True,
                 modal_weight: float = 1.0, masks: Optional[dict] = None, faithful: bool = False,
-                collect: Optional[dict] = None) -> Tensor:
+                collect: Optional[dict] = None, att_type: str = "concat_subsequently") -> Tensor:
     """Returns log_prob (N, C).  ``masks`` (all optional, pre-scaled by 1/(1-p)):
     'gru_l' (T,B,200), 'gru_p' {'a'|'v'|'l': [S x (T,B,200)]}, 'gcn' (see gcnii_stack),
     'head' (N,900)."""
@@ -390,6 +390,8 @@ def forward_gdf(P: Dict[str, Tensor], textf: Tensor, qmask: Tensor, lengths: Seq
                   mk.get("gcn"), faithful, collect)
     if collect is not None:
         collect["emotions_feat"] = feat
+    if att_type == "mfn":
+        return mfn_head(feat, lengths, P, mk)
     return head(feat, P["smax_fc.weight"], P["smax_fc.bias"], mk.get("head"))
 
 
@@ -519,12 +521,14 @@ def mfn_lstm_cell(x: Tensor, h: Tensor, c: Tensor, P: Dict[str, Tensor], prefix:
     return torch.sigmoid(o) * torch.tanh(c2), c2
 
 
-def mfn_forward(x: Tensor, P: Dict[str, Tensor], prefix: str = "") -> Tensor:
-    """Dropout-free restatement of MFN.forward (code/model_fusion.py:62-120).  x (T, n, 900) = [l | a | v] (300 each)
+def mfn_forward(x: Tensor, P: Dict[str, Tensor], prefix: str = "", masks: Optional[Sequence[Tensor]] = None) -> Tensor:
+    """Restatement of MFN.forward (code/model_fusion.py:62-120).  x (T, n, 900) = [l | a | v] (300 each)
     -> (T, n, 400) = [h_l | h_a | h_v | mem].  Three LSTMCells run independently of the memory; per step the window
     cStar = [c_{t-1} | c_t] (600) is re-weighted by a softmax attention (att1), squashed to the memory proposal cHat
     (att2, tanh), and two sigmoid gates computed from [attended | mem_{t-1}] (gamma1, gamma2) update the 100-d memory:
-    mem_t = gamma1 * mem_{t-1} + gamma2 * cHat.  (out_fc1 / out_fc2 are constructed but never used.)"""
+    mem_t = gamma1 * mem_{t-1} + gamma2 * cHat.  (out_fc1 / out_fc2 are constructed but never used.)
+    ``masks``: None (eval: the four Dropout(0.2) layers are identities) or four pre-scaled float masks (T, n, 100)
+    multiplying the ReLU outputs of att1_fc1, att2_fc1, gamma1_fc1, gamma2_fc1 (:92,94,96,97)."""
     pre = (prefix + ".") if prefix else ""
     lin = lambda name, z: linear(z, P[f"{pre}{name}.weight"], P[f"{pre}{name}.bias"])
     T, n = x.shape[0], x.shape[1]
@@ -533,20 +537,39 @@ def mfn_forward(x: Tensor, P: Dict[str, Tensor], prefix: str = "") -> Tensor:
     c = {m: x.new_zeros(n, 100) for m in "lav"}
     mem = x.new_zeros(n, 100)
     outs = []
+    drop = (lambda i, t, z: z * masks[i][t]) if masks is not None else (lambda i, t, z: z)
     for t in range(T):
         prev_cs = torch.cat([c["l"], c["a"], c["v"]], dim=1)
         for m in "lav":
             h[m], c[m] = mfn_lstm_cell(xs[m][t], h[m], c[m], P, f"{pre}lstm_{m}")
         c_star = torch.cat([prev_cs, c["l"], c["a"], c["v"]], dim=1)
-        attention = torch.softmax(lin("att1_fc2", torch.relu(lin("att1_fc1", c_star))), dim=1)
+        attention = torch.softmax(lin("att1_fc2", drop(0, t, torch.relu(lin("att1_fc1", c_star)))), dim=1)
         attended = attention * c_star
-        c_hat = torch.tanh(lin("att2_fc2", torch.relu(lin("att2_fc1", attended))))
+        c_hat = torch.tanh(lin("att2_fc2", drop(1, t, torch.relu(lin("att2_fc1", attended)))))
         both = torch.cat([attended, mem], dim=1)
-        gamma1 = torch.sigmoid(lin("gamma1_fc2", torch.relu(lin("gamma1_fc1", both))))
-        gamma2 = torch.sigmoid(lin("gamma2_fc2", torch.relu(lin("gamma2_fc1", both))))
+        gamma1 = torch.sigmoid(lin("gamma1_fc2", drop(2, t, torch.relu(lin("gamma1_fc1", both)))))
+        gamma2 = torch.sigmoid(lin("gamma2_fc2", drop(3, t, torch.relu(lin("gamma2_fc1", both)))))
         mem = gamma1 * mem + gamma2 * c_hat
         outs.append(torch.cat([h["l"], h["a"], h["v"], mem], dim=-1))
     return torch.stack(outs)
+
+
+def mfn_head(feat: Tensor, lengths: Sequence[int], P: Dict[str, Tensor], masks: Optional[dict] = None) -> Tensor:
+    """att_type 'mfn' after the graph model (code/model.py:1303-1330): node features (N, 900) padded per dialogue to the
+    time-major window (T, B, 900), MFN, valid rows back in node order, dropout -> ReLU -> smax_fc (400 -> C) ->
+    log_softmax.  masks: {'mfn': four pre-scaled (T, B, 100) masks, 'mfn_head': pre-scaled (N, 400)}."""
+    mk = masks or {}
+    T, B = int(max(lengths)), len(lengths)
+    x = feat.new_zeros(T, B, feat.shape[1])
+    off = 0
+    for b, L in enumerate(lengths):
+        x[:L, b] = feat[off:off + L]
+        off += L
+    out = mfn_forward(x, P, "mfn", mk.get("mfn"))
+    rows = torch.cat([out[:L, b] for b, L in enumerate(lengths)], dim=0)
+    if mk.get("mfn_head") is not None:
+        rows = rows * mk["mfn_head"]
+    return torch.log_softmax(linear(torch.relu(rows), P["smax_fc.weight"], P["smax_fc.bias"]), 1)
 
 
 # --------------------------------------------------------------------------------------

@@ -67,7 +67,11 @@ def test_unsupported_configurations_raise():
         mmdfn_b200.DialogueGNNModel("LSTM", 100, 150, 150, 100, 100, 100, 100, 2, 200, 10, 10, graph_type="GDF")
     with pytest.raises(NotImplementedError):
         mmdfn_b200.DialogueGNNModel("LSTM", 100, 150, 150, 100, 100, 100, 100, 2, 200, 10, 10, graph_type="relation",
-                                    att_type="mfn")
+                                    att_type="tfn_only")
+    m = mmdfn_b200.DialogueGNNModel("LSTM", 100, 150, 150, 100, 100, 100, 100, 2, 200, 10, 10, graph_type="GDF", n_classes=6,
+                                    att_type="mfn", Deep_GCN_nlayers=2)
+    assert tuple(m.smax_fc.weight.shape) == (6, 400)          # code/model.py:991-994: 3 x 100 hidden states + the 100-d memory
+    assert [k for k in m.state_dict() if k.startswith("mfn.")][:2] == ["mfn.lstm_l.weight_ih", "mfn.lstm_l.weight_hh"]
     m = mmdfn_b200.DialogueGNNModel("LSTM", 100, 150, 150, 100, 100, 100, 100, 2, 200, 10, 10, graph_type="relation",
                                     n_classes=6)              # defaults: att_type='gated' -> 300-wide classifier input
     assert tuple(m.smax_fc.weight.shape) == (6, 300)          # code/model.py:986-988
