@@ -10,20 +10,6 @@ namespace mmdfn {
 constexpr int HF = 300;     // per-modality feature width [x200 | g100]
 constexpr int MAXC = 16;
 
-// R[(m*N+n), k] = relu(F[(m*N+n), k] * mask[n, m*300+k] * scale)
-__global__ void head_relu_kernel(int N, const float* __restrict__ F, const unsigned char* __restrict__ mask,
-                                 float scale, int relu, float* __restrict__ R) {
-  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (i64)3 * N * HF) return;
-  const i64 row = idx / HF;
-  const int k = (int)(idx - row * HF);
-  const int m = (int)(row / N);
-  const i64 n = row - (i64)m * N;
-  float v = F[idx];
-  if (mask) v = mask[n * 900 + m * HF + k] ? v * scale : 0.f;
-  R[idx] = relu ? fmaxf(v, 0.f) : v;
-}
-
 // in-place row-wise log_softmax over C (thread per row)
 __global__ void log_softmax_kernel(int N, int C, const float* logits, float* out) {   // in place allowed
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,21 +33,164 @@ __global__ void log_softmax_bwd_kernel(int N, int C, const float* __restrict__ l
   for (int c = 0; c < C; c++) dlogits[(i64)n * C + c] = dlp[(i64)n * C + c] - expf(lp[(i64)n * C + c]) * s;
 }
 
-// dF = dR * [relu ? R > 0 : 1] * (mask ? keep * scale : 1), in place on dF
-__global__ void head_relu_bwd_kernel(int N, const float* __restrict__ R, const unsigned char* __restrict__ mask,
-                                     float scale, int relu, float* __restrict__ dF) {
-  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (i64)3 * N * HF) return;
-  float g = dF[idx];
-  if (mask) {
-    const i64 row = idx / HF;
-    const int k = (int)(idx - row * HF);
-    const int m = (int)(row / N);
-    const i64 n = row - (i64)m * N;
-    g = mask[n * 900 + m * HF + k] ? g * scale : 0.f;
+// ---- fused head (round 2): one launch for the forward, two for the backward ---------------------------------------
+// The head is 3N x 300 inputs against a (C, 900) weight with C <= 16: ~11 MFLOP over 11.5 MB -- an HBM-bound row
+// reduction, not a GEMM.  Forward: one warp per utterance walks its three 300-wide segments with 128-bit loads, applies
+// keep * scale and ReLU, stores R (saved for the backward), accumulates the C dot products against the weight held in
+// shared memory, reduces them over the warp and writes log_softmax.  Backward kernel 1 (warp per utterance): dlogits
+// (stored for kernel 2) and dF = (dlogits Wc) * keep * scale * [R > 0].  Backward kernel 2: dWc / dbc as column-parallel
+// sums over row chunks (a thread owns one of the 900 (+1 bias) columns), combined with atomics into zeroed targets.
+template <int CT>
+__global__ void __launch_bounds__(256) head_fused_fwd_kernel(int N, int C, const float* __restrict__ F,
+                                                              const unsigned char* __restrict__ mask, float scale, int relu,
+                                                              const float* __restrict__ Wc, const float* __restrict__ bc,
+                                                              float* __restrict__ R, float* __restrict__ lp) {
+  extern __shared__ __align__(16) float wsm[];                // (C, 900)
+  for (int i = threadIdx.x; i < C * 900; i += blockDim.x) wsm[i] = Wc[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
+    float acc[CT];
+#pragma unroll
+    for (int c = 0; c < CT; c++) acc[c] = 0.f;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const i64 rb = ((i64)m * N + n) * HF;
+#pragma unroll
+      for (int it = 0; it < 3; it++) {
+        const int g = lane + 32 * it;                          // float4 group of the 300-wide segment (75 groups)
+        if (g < 75) {
+          float4 v = ldg_stream4(F + rb + 4 * g);
+          if (mask) {
+            const uint32_t mk = *reinterpret_cast<const uint32_t*>(mask + (i64)n * 900 + m * HF + 4 * g);
+            v.x = (mk & 0xFFu) ? v.x * scale : 0.f;
+            v.y = (mk & 0xFF00u) ? v.y * scale : 0.f;
+            v.z = (mk & 0xFF0000u) ? v.z * scale : 0.f;
+            v.w = (mk & 0xFF000000u) ? v.w * scale : 0.f;
+          }
+          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          *reinterpret_cast<float4*>(R + rb + 4 * g) = v;
+#pragma unroll
+          for (int c = 0; c < CT; c++) {
+            if (c < C) {
+              const float4 w = *reinterpret_cast<const float4*>(wsm + c * 900 + m * HF + 4 * g);
+              acc[c] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[c]))));
+            }
+          }
+        }
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CT; c++) {
+      acc[c] = warp_sum(acc[c]) + (c < C ? bc[c] : 0.f);
+      if (c < C) mx = fmaxf(mx, acc[c]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CT; c++)
+      if (c < C) s += expf(acc[c] - mx);
+    const float lse = mx + logf(s);
+#pragma unroll
+    for (int c = 0; c < CT; c++)
+      if (c == lane && c < C) lp[(i64)n * C + c] = acc[c] - lse;
   }
-  if (relu && !(R[idx] > 0.f)) g = 0.f;
-  dF[idx] = g;
+}
+
+template <int CT>
+__global__ void __launch_bounds__(256) head_fused_bwd_kernel(int N, int C, const unsigned char* __restrict__ mask, float scale,
+                                                              int relu, const float* __restrict__ Wc, const float* __restrict__ R,
+                                                              const float* __restrict__ lp, const float* __restrict__ dlp,
+                                                              float* __restrict__ dF, float* __restrict__ dlogits) {
+  extern __shared__ __align__(16) float wsm[];
+  for (int i = threadIdx.x; i < C * 900; i += blockDim.x) wsm[i] = Wc[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
+    float dl[CT];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CT; c++) {
+      dl[c] = c < C ? dlp[(i64)n * C + c] : 0.f;
+      sum += dl[c];
+    }
+#pragma unroll
+    for (int c = 0; c < CT; c++) {
+      if (c < C) dl[c] -= expf(lp[(i64)n * C + c]) * sum;
+      if (c == lane && c < C) dlogits[(i64)n * C + c] = dl[c];
+    }
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const i64 rb = ((i64)m * N + n) * HF;
+#pragma unroll
+      for (int it = 0; it < 3; it++) {
+        const int g = lane + 32 * it;
+        if (g < 75) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < CT; c++) {
+            if (c < C) {
+              const float4 w = *reinterpret_cast<const float4*>(wsm + c * 900 + m * HF + 4 * g);
+              a.x = fmaf(dl[c], w.x, a.x); a.y = fmaf(dl[c], w.y, a.y); a.z = fmaf(dl[c], w.z, a.z); a.w = fmaf(dl[c], w.w, a.w);
+            }
+          }
+          if (mask) {
+            const uint32_t mk = *reinterpret_cast<const uint32_t*>(mask + (i64)n * 900 + m * HF + 4 * g);
+            a.x = (mk & 0xFFu) ? a.x * scale : 0.f;
+            a.y = (mk & 0xFF00u) ? a.y * scale : 0.f;
+            a.z = (mk & 0xFF0000u) ? a.z * scale : 0.f;
+            a.w = (mk & 0xFF000000u) ? a.w * scale : 0.f;
+          }
+          if (relu) {
+            const float4 r = ldg_stream4(R + rb + 4 * g);
+            if (!(r.x > 0.f)) a.x = 0.f;
+            if (!(r.y > 0.f)) a.y = 0.f;
+            if (!(r.z > 0.f)) a.z = 0.f;
+            if (!(r.w > 0.f)) a.w = 0.f;
+          }
+          *reinterpret_cast<float4*>(dF + rb + 4 * g) = a;
+        }
+      }
+    }
+  }
+}
+
+// dWc[c][j] += sum_n dlogits[n][c] R[n][j]  (j < 900; column 900 = the bias gradient), rows chunked over blockIdx.y
+constexpr int HW_ROWS = 64;
+template <int CT>
+__global__ void __launch_bounds__(128) head_wgrad_kernel(int N, int C, const float* __restrict__ R, const float* __restrict__ dlogits,
+                                                          float* __restrict__ dWc, float* __restrict__ dbc) {
+  __shared__ float dls[HW_ROWS * CT];
+  const int n0 = blockIdx.y * HW_ROWS, rows = min(HW_ROWS, N - n0);
+  for (int i = threadIdx.x; i < rows * C; i += blockDim.x) dls[(i / C) * CT + (i % C)] = dlogits[(i64)n0 * C + i];
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > 900) return;
+  float acc[CT];
+#pragma unroll
+  for (int c = 0; c < CT; c++) acc[c] = 0.f;
+  if (j < 900) {
+    const int m = j / HF, k = j - m * HF;
+    const float* rp = R + ((i64)m * N + n0) * HF + k;
+#pragma unroll 4
+    for (int r = 0; r < rows; r++) {
+      const float v = rp[(i64)r * HF];
+#pragma unroll
+      for (int c = 0; c < CT; c++) acc[c] = fmaf(dls[r * CT + c], v, acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < CT; c++)
+      if (c < C) atomicAdd(dWc + c * 900 + j, acc[c]);
+  } else {
+    for (int r = 0; r < rows; r++)
+#pragma unroll
+      for (int c = 0; c < CT; c++) acc[c] += dls[r * CT + c];
+#pragma unroll
+    for (int c = 0; c < CT; c++)
+      if (c < C) atomicAdd(dbc + c, acc[c]);
+  }
 }
 
 // loss = (mean|sum)_n -(1-pt)^gamma * alpha[y] * lp[n,y],  pt = exp(lp[n,y]) (no gradient through pt)
@@ -180,18 +309,36 @@ __global__ void adam_kernel(i64 n, float* __restrict__ p, const float* __restric
 
 using namespace mmdfn;
 
+// one-time opt-in to > 48 KB of dynamic shared memory (C = 14..16 classes); returns the SM count
+static int head_init(int* sms_out) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, n = 0;
+    MMDFN_CUDA(cudaGetDevice(&dev));
+    MMDFN_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    MMDFN_CUDA(cudaFuncSetAttribute(head_fused_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXC * 900 * 4));
+    MMDFN_CUDA(cudaFuncSetAttribute(head_fused_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXC * 900 * 4));
+    MMDFN_CUDA(cudaFuncSetAttribute(head_fused_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXC * 900 * 4));
+    MMDFN_CUDA(cudaFuncSetAttribute(head_fused_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXC * 900 * 4));
+    sms = n;
+  }
+  *sms_out = sms;
+  return 0;
+}
+
 extern "C" int mmdfn_head_fwd(int N, int C, const float* F, const unsigned char* mask, float mask_scale, int relu,
                               const float* Wc, const float* bc, float* R, float* log_prob, void* stream) {
   if (!F || !Wc || !bc || !R || !log_prob) return MMDFN_ENULL;
   if (C <= 0 || C > MAXC || N < 0) return MMDFN_EINVAL;
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  head_relu_kernel<<<(unsigned)ceil_div64((i64)3 * N * HF, 256), 256, 0, st>>>(N, F, mask, mask_scale, relu, R);
-  MMDFN_LAUNCH_CHECK();
-  for (int m = 0; m < 3; m++)
-    MMDFN_TRY(gemm(false, true, N, C, HF, 1.f, R + (i64)m * N * HF, HF, Wc + m * HF, 3 * HF, m ? 1.f : 0.f, log_prob, C,
-                   m ? nullptr : bc, 0, st));
-  log_softmax_kernel<<<ceil_div(N, 128), 128, 0, st>>>(N, C, log_prob, log_prob);
+  int sms = 0;
+  MMDFN_TRY(head_init(&sms));
+  if (((uintptr_t)F | (uintptr_t)R) & 15 || (mask && ((uintptr_t)mask & 3))) return MMDFN_EINVAL;
+  const int grid = min(2 * sms, ceil_div(N, 8));
+  const size_t smem = (size_t)C * 900 * sizeof(float);
+  if (C <= 8) head_fused_fwd_kernel<8><<<grid, 256, smem, st>>>(N, C, F, mask, mask_scale, relu, Wc, bc, R, log_prob);
+  else head_fused_fwd_kernel<16><<<grid, 256, smem, st>>>(N, C, F, mask, mask_scale, relu, Wc, bc, R, log_prob);
   MMDFN_LAUNCH_CHECK();
   return 0;
 }
@@ -203,20 +350,30 @@ extern "C" int mmdfn_head_bwd(int N, int C, const unsigned char* mask, float mas
   if (!Wc || !R || !log_prob || !dlog_prob || !dF || !dWc || !dbc || !dlogits_ws) return MMDFN_ENULL;
   if (C <= 0 || C > MAXC || N < 0) return MMDFN_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  const float gb = grads_zeroed ? 1.f : 0.f;
   if (N == 0) {
     if (grads_zeroed) return 0;
     MMDFN_TRY(fill_zero(dWc, (size_t)C * 900 * sizeof(float), st));
     return fill_zero(dbc, (size_t)C * sizeof(float), st);
   }
-  log_softmax_bwd_kernel<<<ceil_div(N, 128), 128, 0, st>>>(N, C, log_prob, dlog_prob, dlogits_ws);
-  MMDFN_LAUNCH_CHECK();
-  MMDFN_TRY(colsum(N, C, dlogits_ws, C, gb, dbc, st));
-  for (int m = 0; m < 3; m++) {
-    MMDFN_TRY(gemm(true, false, C, HF, N, 1.f, dlogits_ws, C, R + (i64)m * N * HF, HF, gb, dWc + m * HF, 3 * HF, nullptr, 0, st));
-    MMDFN_TRY(gemm(false, false, N, HF, C, 1.f, dlogits_ws, C, Wc + m * HF, 3 * HF, 0.f, dF + (i64)m * N * HF, HF, nullptr, 0, st));
+  if (!grads_zeroed) {
+    MMDFN_TRY(fill_zero(dWc, (size_t)C * 900 * sizeof(float), st));
+    MMDFN_TRY(fill_zero(dbc, (size_t)C * sizeof(float), st));
   }
-  head_relu_bwd_kernel<<<(unsigned)ceil_div64((i64)3 * N * HF, 256), 256, 0, st>>>(N, R, mask, mask_scale, relu, dF);
+  if (((uintptr_t)dF | (uintptr_t)R) & 15 || (mask && ((uintptr_t)mask & 3))) return MMDFN_EINVAL;
+  int sms = 0;
+  MMDFN_TRY(head_init(&sms));
+  const int grid = min(2 * sms, ceil_div(N, 8));
+  const size_t smem = (size_t)C * 900 * sizeof(float);
+  const dim3 wg(ceil_div(901, 128), ceil_div(N, HW_ROWS));
+  if (C <= 8) {
+    head_fused_bwd_kernel<8><<<grid, 256, smem, st>>>(N, C, mask, mask_scale, relu, Wc, R, log_prob, dlog_prob, dF, dlogits_ws);
+    MMDFN_LAUNCH_CHECK();
+    head_wgrad_kernel<8><<<wg, 128, 0, st>>>(N, C, R, dlogits_ws, dWc, dbc);
+  } else {
+    head_fused_bwd_kernel<16><<<grid, 256, smem, st>>>(N, C, mask, mask_scale, relu, Wc, R, log_prob, dlog_prob, dF, dlogits_ws);
+    MMDFN_LAUNCH_CHECK();
+    head_wgrad_kernel<16><<<wg, 128, 0, st>>>(N, C, R, dlogits_ws, dWc, dbc);
+  }
   MMDFN_LAUNCH_CHECK();
   return 0;
 }

@@ -29,9 +29,20 @@ def step(i):
     return trainer.step(t, q, u, lengths, a, v, lab, sum(lengths))
 
 
+GRAPH = "--graph" in sys.argv          # profile replays of the captured whole-step graph (the bench's launch mode)
 for i in range(5):
     step(i)
 torch.cuda.synchronize()
+if GRAPH:
+    t, a, v, q, u, lab = batches[0]
+    trainer.capture(t, q, u, lengths, a, v, lab, sum(lengths), warmup=0)
+
+    def step(i):
+        t, a, v, q, u, lab = batches[i % 2]
+        return trainer.replay(t, q, u, a, v, lab, lengths)
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
 NSTEP = 4
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
@@ -43,7 +54,7 @@ prof.export_chrome_trace(out)
 ev = [e for e in json.load(open(out))["traceEvents"] if e.get("cat") == "kernel"]
 ev.sort(key=lambda e: e["ts"])
 # keep the last step: kernels after the (NSTEP-1)th adam kernel
-adam = [i for i, e in enumerate(ev) if "adam_kernel" in e["name"]]
+adam = [i for i, e in enumerate(ev) if "adam_kernel" in e["name"] or "adam_dev_kernel" in e["name"]]
 last = ev[adam[-2] + 1: adam[-1] + 1]
 t0, t1 = last[0]["ts"], last[-1]["ts"] + last[-1]["dur"]
 print("last step: %d kernels, span %.1f us" % (len(last), t1 - t0))
