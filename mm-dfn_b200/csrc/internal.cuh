@@ -15,6 +15,13 @@ int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A
 bool umma_gemm2_eligible(bool ta, bool tb, int M, int N, int K, const float* A, i64 lda, const float* B, i64 ldb);
 int umma_gemm2(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64 lda, const float* B, i64 ldb,
                float beta, float* C, i64 ldc, const float* bias, int act, int splits, cudaStream_t st);
+// third-generation tcgen05 kernel (A operand in tensor memory, one wide CTA per SM; umma_gemm3.cu)
+bool umma_gemm3_eligible(bool ta, bool tb, int M, int N, int K, const float* A, i64 lda, const float* B, i64 ldb);
+int umma_gemm3_splits(int M, int N, int K, bool plain_epilogue);
+void umma_gemm3_set_debug(int v);
+void umma_gemm3_set_stamps(long long* device_buf);
+int umma_gemm3(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64 lda, const float* B, i64 ldb,
+               float beta, float* C, i64 ldc, const float* bias, int act, int splits, cudaStream_t st);
 // out[n] = beta*out[n] + sum_m A[m*lda + n]
 int colsum(int M, int N, const float* A, i64 lda, float beta, float* out, cudaStream_t st);
 int fill_zero(void* p, size_t bytes, cudaStream_t st);

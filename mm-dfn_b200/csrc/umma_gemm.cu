@@ -480,6 +480,19 @@ int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A
   if (!A || !B || !C) return MMDFN_ENULL;
   if (tb && ta) return MMDFN_EINVAL;
   UGemmArgs p{A, lda, B, ldb, C, ldc, bias, M, N, K, alpha, beta, act, 1, g_ug_variant, g_ug_dbg};
+  // third generation (A operand in tensor memory, one wide CTA per SM, coalesced epilogue; umma_gemm3.cu): the default
+  // for every form whose K-contiguous operands are 16-byte aligned.  mmdfn_gemm_tc_set_variant: 1 = first generation
+  // only, 2 = second generation where eligible, 112 / 160 / 224 = first generation with a forced column tile (A/B timing).
+  if (g_ug_variant == 0 || g_ug_variant == 3) {
+    if (umma_gemm3_eligible(ta, tb, M, N, K, A, lda, B, ldb)) {
+      const int sp = umma_gemm3_splits(M, N, K, bias == nullptr && act == 0);
+      if (sp > 1 && beta != 1.f) {
+        ug_scale2d_kernel<<<(unsigned)ceil_div64((i64)M * N, 256), 256, 0, st>>>(C, ldc, M, N, beta);
+        MMDFN_LAUNCH_CHECK();
+      }
+      return umma_gemm3(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act, sp, st);
+    }
+  }
   // column tile: 112 unless a width is forced through mmdfn_gemm_tc_set_variant (profiling aid)
   int bn = 112;
   if (g_ug_variant == 112 || g_ug_variant == 160 || g_ug_variant == 224) {
@@ -518,10 +531,17 @@ int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A
 // profiling aid: device buffer of 128 int64 receiving clock64() phase stamps of CTA 0 (nullptr switches it off)
 extern "C" int mmdfn_gemm_tc_set_debug(long long* device_buf) {
   mmdfn::g_ug_dbg = device_buf;
+  mmdfn::umma_gemm3_set_stamps(device_buf);
   return 0;
 }
 
 extern "C" int mmdfn_gemm_tc_set_variant(int v) {
+  if (v >= 30 && v < 40) {                 // third generation with a profiling switch (umma_gemm3.cu)
+    mmdfn::umma_gemm3_set_debug(v - 30);
+    v = 3;
+  } else {
+    mmdfn::umma_gemm3_set_debug(0);
+  }
   mmdfn::g_ug_variant = v;
   return 0;
 }

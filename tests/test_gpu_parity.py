@@ -41,8 +41,9 @@ def relerr(a, b):
 # ---------------------------------------------------------------------------------------------
 @pytest.fixture(params=[0, 1, 2], autouse=False)
 def gemm_variant(request):
-    """0 = default dispatch (second-generation tcgen05 kernel for aligned NT problems), 1 = first generation only,
-    2 = second generation for every eligible form (its NN / TN operand paths: TMA raw ring + transposed reads)"""
+    """0 = default dispatch (third-generation tcgen05 kernel -- A operand in tensor memory -- wherever the K-contiguous
+    operands are 16-byte aligned, first generation otherwise), 1 = first generation only, 2 = second generation for
+    every eligible form (register / TMA raw-ring operand paths)"""
     from mmdfn_b200 import _lib
     _lib.call("mmdfn_gemm_tc_set_variant", request.param)
     yield request.param

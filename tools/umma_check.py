@@ -58,7 +58,7 @@ run("TN dW_ih splitK", 1, 0, 300, 200, 19200)
 run("TN dW small", 1, 0, 100, 100, 9600, beta=1.0)
 run("TN dW proj", 1, 0, 200, 1024, 3200)
 run("TN ragged", 1, 0, 77, 45, 190)
-print("=== generation 1 (cp.async staging ring) vs generation 2 (register / TMA operand paths): us per launch")
+print("=== generation 1 (cp.async staging ring) / 2 (register / TMA operand paths) / 3 (A operand in tensor memory, wide CTA): us per launch")
 def timed(ta, tb, M, N, K, variant, beta=0.0):
     A = torch.randn((K, M) if ta else (M, K), device=dev); B = torch.randn((N, K) if tb else (K, N), device=dev); C = torch.zeros(M, N, device=dev)
     L.call("mmdfn_gemm_tc_set_variant", variant)
@@ -77,11 +77,13 @@ def timed(ta, tb, M, N, K, variant, beta=0.0):
 for name, ta, tb, M, N, K in (("NT proj audio", 0, 1, 3200, 200, 512), ("NT proj visual", 0, 1, 3200, 200, 1024), ("NT gru in-gemm party", 0, 1, 9600, 600, 200),
                               ("NT gru in-gemm", 0, 1, 19200, 300, 200), ("NT lstm gates", 0, 1, 9600, 400, 100), ("NT big", 0, 1, 153600, 300, 200),
                               ("NN dx", 0, 0, 19200, 200, 300), ("NN dgates W", 0, 0, 9600, 100, 400), ("NN R_all", 0, 0, 9600, 200, 100),
-                              ("TN dW_ih splitK", 1, 0, 300, 200, 19200), ("TN dW gates", 1, 0, 400, 100, 9600), ("TN dW proj", 1, 0, 200, 1024, 3200)):
-    t1, t2 = timed(ta, tb, M, N, K, 1), timed(ta, tb, M, N, K, 2)
+                              ("TN dW_ih splitK", 1, 0, 300, 200, 19200), ("TN dW gates", 1, 0, 400, 100, 9600), ("TN dW proj", 1, 0, 200, 1024, 3200),
+                              ("NT proj text", 0, 1, 3200, 200, 100), ("NN dx party l0", 0, 0, 9600, 200, 600), ("TN dW_ih l1 both", 1, 0, 600, 200, 19200)):
+    t1, t2, t3 = timed(ta, tb, M, N, K, 1), timed(ta, tb, M, N, K, 2), timed(ta, tb, M, N, K, 3)
     gf = 2.0 * M * N * K / 1e9
-    print(f"{name:24s} M={M:6d} N={N:4d} K={K:6d}  gen1 {t1:7.1f} us ({gf/t1*1e3:6.1f} TF/s)   gen2 {t2:7.1f} us ({gf/t2*1e3:6.1f} TF/s)   x{t1/t2:.2f}", flush=True)
-for bn in (112, 160, 224):
+    print(f"{name:24s} M={M:6d} N={N:4d} K={K:6d}  gen1 {t1:7.1f} us ({gf/t1*1e3:6.1f} TF/s)   gen2 {t2:7.1f} us ({gf/t2*1e3:6.1f} TF/s)   "
+          f"gen3 {t3:7.1f} us ({gf/t3*1e3:6.1f} TF/s)   gen3 vs best x{min(t1, t2)/t3:.2f}", flush=True)
+for bn in (() if "--quick" in sys.argv else (112, 160, 224)):
     L.call("mmdfn_gemm_tc_set_variant", bn)
     print(f"--- forced BN={bn}")
     run("NT gru in-gemm", 0, 1, 19200, 300, 200, bias=True)
