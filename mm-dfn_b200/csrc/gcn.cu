@@ -83,6 +83,36 @@ __global__ void copy2d_mask_kernel(i64 rows, int cols, const float* __restrict__
   dst[r * dld + c] = v;
 }
 
+// the same copy, four columns per thread (cols, both leading dimensions multiples of 4; 16-byte aligned pointers)
+__global__ void copy2d_mask4_kernel(i64 rows, int cols4, const float* __restrict__ src, i64 sld,
+                                    const unsigned char* __restrict__ mask, float scale, float* __restrict__ dst,
+                                    i64 dld) {
+  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols4) return;
+  const i64 r = idx / cols4;
+  const int c = 4 * (int)(idx - r * cols4);
+  float4 v = *reinterpret_cast<const float4*>(src + r * sld + c);
+  if (mask) {
+    const uint32_t k = *reinterpret_cast<const uint32_t*>(mask + 4 * idx);
+    v.x = (k & 0xFFu) ? v.x * scale : 0.f;
+    v.y = (k & 0xFF00u) ? v.y * scale : 0.f;
+    v.z = (k & 0xFF0000u) ? v.z * scale : 0.f;
+    v.w = (k & 0xFF000000u) ? v.w * scale : 0.f;
+  }
+  *reinterpret_cast<float4*>(dst + r * dld + c) = v;
+}
+
+static int copy2d_mask(i64 rows, int cols, const float* src, i64 sld, const unsigned char* mask, float scale, float* dst,
+                       i64 dld, cudaStream_t st) {
+  const bool vec = (cols & 3) == 0 && (sld & 3) == 0 && (dld & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(mask) & 3) == 0;
+  if (vec) copy2d_mask4_kernel<<<(unsigned)ceil_div64(rows * (cols / 4), 256), 256, 0, st>>>(rows, cols / 4, src, sld, mask, scale, dst, dld);
+  else copy2d_mask_kernel<<<(unsigned)ceil_div64(rows * cols, 256), 256, 0, st>>>(rows, cols, src, sld, mask, scale, dst, dld);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
+}
+
 // dpre = (dh0 + dz0*mask*scale) * [h0 > 0]
 __global__ void h0_bwd_kernel(i64 n, const float* __restrict__ dh0, const float* __restrict__ dz0,
                               const unsigned char* __restrict__ mask, float scale, const float* __restrict__ h0,
@@ -161,15 +191,12 @@ extern "C" int mmdfn_gcn_stack_fwd(int B, int N, int Lmax, const int* dia_off, c
   float* pre = ws + w.pre;
   const i64 ldk = (i64)GG * K;
   // x_d = dropout(X) stored straight into F[:, 0:200]                           (model_GCN.py:453,483)
-  copy2d_mask_kernel<<<nblk(n3 * GX), 256, 0, st>>>(n3, GX, X, GX, mask_x, mask_scale, F, GF);
-  MMDFN_LAUNCH_CHECK();
+  MMDFN_TRY(copy2d_mask(n3, GX, X, GX, mask_x, mask_scale, F, GF, st));
   // h0 = relu(x_d W0^T + b0)                                                     (:454)
   MMDFN_TRY(gemm(false, true, (int)n3, GG, GX, 1.f, F, GF, W0, GX, 0.f, h0, GG, b0, 1, st));
-  copy2d_mask_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3, GG, h0, GG, mask_h0, mask_scale, z0, GG);   // (:456)
-  MMDFN_LAUNCH_CHECK();
+  MMDFN_TRY(copy2d_mask(n3, GG, h0, GG, mask_h0, mask_scale, z0, GG, st));   // (:456)
   if (K == 0) {
-    copy2d_mask_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3, GG, z0, GG, nullptr, 1.f, F + GX, GF);    // (:482-483)
-    MMDFN_LAUNCH_CHECK();
+    MMDFN_TRY(copy2d_mask(n3, GG, z0, GG, nullptr, 1.f, F + GX, GF, st));    // (:482-483)
     return 0;
   }
   if (reason_flag) MMDFN_TRY(fill_zero(zeros, (size_t)n3 * GG * sizeof(float), st));
@@ -256,8 +283,7 @@ extern "C" int mmdfn_gcn_stack_bwd(int B, int N, int Lmax, const int* dia_off, c
   float* dmbot_all = dmtop_all + (i64)GG * ldk;
   const float scale = mask_layers ? mask_scale : 1.f;
   // dz_K = dF[:, 200:300]
-  copy2d_mask_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3, GG, dF + GX, GF, nullptr, 1.f, dz, GG);
-  MMDFN_LAUNCH_CHECK();
+  MMDFN_TRY(copy2d_mask(n3, GG, dF + GX, GF, nullptr, 1.f, dz, GG, st));
   if (K == 0) MMDFN_TRY(fill_zero(dh0, (size_t)n3 * GG * sizeof(float), st));
   else MMDFN_TRY(fill_zero(dmtop_all, (size_t)2 * GG * ldk * sizeof(float), st));      // dMtop_all | dMbot_all: split-K targets
   const float gb = grads_zeroed ? 1.f : 0.f;     // caller pre-zeroed every gradient buffer: accumulate, no zero-init launches

@@ -301,14 +301,46 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __
   if (slot >= nslots) return;
   const int row = rowmap[slot];
   if (row < 0) return;
-  for (int c = threadIdx.x; c < 600; c += 32) atomicAdd(dst + (i64)row * 600 + c, src[slot * 600 + c]);
+  const float* s = src + slot * 600;
+  float* d = dst + (i64)row * 600;
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    for (int c = threadIdx.x; c < 150; c += 32) {            // 128-bit loads and vector reductions: 150 per row instead of 600
+      const float4 v = *reinterpret_cast<const float4*>(s + 4 * c);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4 * c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+  } else {
+    for (int c = threadIdx.x; c < 600; c += 32) atomicAdd(d + c, s[c]);
+  }
 }
 
 // y = x * mask * scale (uint8 mask); in == out allowed
 __global__ void mask_mul_kernel(const float* __restrict__ x, const unsigned char* __restrict__ m, float scale, i64 n,
                                 float* __restrict__ y) {
+  // n is a multiple of 4 (rows of 200 floats) and all three pointers are 16-byte / 4-byte aligned: 4 elements per thread
+  const i64 i = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const float4 v = *reinterpret_cast<const float4*>(x + i);
+  const uint32_t k = *reinterpret_cast<const uint32_t*>(m + i);
+  float4 o;
+  o.x = (k & 0xFFu) ? v.x * scale : 0.f;
+  o.y = (k & 0xFF00u) ? v.y * scale : 0.f;
+  o.z = (k & 0xFF0000u) ? v.z * scale : 0.f;
+  o.w = (k & 0xFF000000u) ? v.w * scale : 0.f;
+  *reinterpret_cast<float4*>(y + i) = o;
+}
+
+__global__ void mask_mul1_kernel(const float* __restrict__ x, const unsigned char* __restrict__ m, float scale, i64 n,
+                                 float* __restrict__ y) {
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = m[i] ? x[i] * scale : 0.f;
+}
+static int mask_mul(const float* x, const unsigned char* m, float scale, i64 n, float* y, cudaStream_t st) {
+  const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(m) & 3) == 0;
+  if (vec) mask_mul_kernel<<<(unsigned)ceil_div64(n / 4, 256), 256, 0, st>>>(x, m, scale, n, y);
+  else mask_mul1_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(x, m, scale, n, y);
+  MMDFN_LAUNCH_CHECK();
+  return 0;
 }
 
 // Sequences per CTA (NB).  Measured with clock64 stamps (profiles/r01_gru_phase_stamps_s2.log): a step costs about
@@ -402,8 +434,7 @@ extern "C" int mmdfn_bigru2_fwd(int T, int nseq, long long rows, const float* x,
   MMDFN_TRY(launch_gru_fwd(a, st));
   const float* l1in = y1;
   if (mask) {
-    mask_mul_kernel<<<(unsigned)ceil_div64(slots * 200, 256), 256, 0, st>>>(y1, mask, mask_scale, slots * 200, y1d);
-    MMDFN_LAUNCH_CHECK();
+    MMDFN_TRY(mask_mul(y1, mask, mask_scale, slots * 200, y1d, st));
     l1in = y1d;
   }
   MMDFN_TRY(gemm(false, true, (int)slots, 300, 200, 1.f, l1in, 200, w[8], 200, 0.f, xg2, 600, w[10], 0, st));
@@ -476,8 +507,7 @@ extern "C" int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x,
   MMDFN_TRY(gemm(false, false, (int)slots, 200, 300, 1.f, dxg, 600, w[8], 200, 0.f, dy1, 200, nullptr, 0, st));
   MMDFN_TRY(gemm(false, false, (int)slots, 200, 300, 1.f, dxg + 300, 600, w[12], 200, 1.f, dy1, 200, nullptr, 0, st));
   if (mask) {
-    mask_mul_kernel<<<(unsigned)ceil_div64(slots * 200, 256), 256, 0, st>>>(dy1, mask, mask_scale, slots * 200, dy1);
-    MMDFN_LAUNCH_CHECK();
+    MMDFN_TRY(mask_mul(dy1, mask, mask_scale, slots * 200, dy1, st));
   }
   // ---- layer 0 ----
   GruBwdArgs a{T, nseq, dy1, y1, gates1, {w[1], w[5]}, dxg, dgh, {dw[2], dw[6]}, {dw[3], dw[7]}};

@@ -40,13 +40,32 @@ __global__ void log_softmax_bwd_kernel(int N, int C, const float* __restrict__ l
 // shared memory, reduces them over the warp and writes log_softmax.  Backward kernel 1 (warp per utterance): dlogits
 // (stored for kernel 2) and dF = (dlogits Wc) * keep * scale * [R > 0].  Backward kernel 2: dWc / dbc as column-parallel
 // sums over row chunks (a thread owns one of the 900 (+1 bias) columns), combined with atomics into zeroed targets.
+// weight (C, 900) -> shared memory: 128-bit loads, all of a thread's loads in flight before the first store (a plain
+// load-store loop paid one global-memory latency per iteration: 21 of them, ~6 us of the kernel's 24)
+__device__ __forceinline__ void head_load_w(float* wsm, const float* __restrict__ Wc, int C) {
+  const int n4 = C * 225;                                     // float4 pieces
+  if ((reinterpret_cast<uintptr_t>(Wc) & 15) == 0) {
+    for (int i0 = threadIdx.x; i0 < n4; i0 += 8 * blockDim.x) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        if (i0 + u * blockDim.x < n4) v[u] = __ldg(reinterpret_cast<const float4*>(Wc) + i0 + u * blockDim.x);
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        if (i0 + u * blockDim.x < n4) reinterpret_cast<float4*>(wsm)[i0 + u * blockDim.x] = v[u];
+    }
+  } else {
+    for (int i = threadIdx.x; i < C * 900; i += blockDim.x) wsm[i] = Wc[i];
+  }
+}
+
 template <int CT>
 __global__ void __launch_bounds__(256) head_fused_fwd_kernel(int N, int C, const float* __restrict__ F,
                                                               const unsigned char* __restrict__ mask, float scale, int relu,
                                                               const float* __restrict__ Wc, const float* __restrict__ bc,
                                                               float* __restrict__ R, float* __restrict__ lp) {
   extern __shared__ __align__(16) float wsm[];                // (C, 900)
-  for (int i = threadIdx.x; i < C * 900; i += blockDim.x) wsm[i] = Wc[i];
+  head_load_w(wsm, Wc, C);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -104,7 +123,7 @@ __global__ void __launch_bounds__(256) head_fused_bwd_kernel(int N, int C, const
                                                               const float* __restrict__ lp, const float* __restrict__ dlp,
                                                               float* __restrict__ dF, float* __restrict__ dlogits) {
   extern __shared__ __align__(16) float wsm[];
-  for (int i = threadIdx.x; i < C * 900; i += blockDim.x) wsm[i] = Wc[i];
+  head_load_w(wsm, Wc, C);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -234,16 +253,34 @@ __global__ void focal_bwd_kernel(int N, int C, const float* __restrict__ lp, con
 }
 
 // counter-based keep mask: keep with probability 1-p; one 64-bit mix per element (splitmix64)
-__global__ void dropout_mask_kernel(i64 n, float p, unsigned long long seed, unsigned long long offset,
-                                    unsigned char* __restrict__ mask) {
-  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  unsigned long long z = seed * 0x9E3779B97F4A7C15ull + (offset + (unsigned long long)idx) * 0xD1342543DE82EF95ull;
+// keep byte of element `idx`: one splitmix64 mix of (seed, counter base + idx)
+__device__ __forceinline__ unsigned int keep_byte(unsigned long long seed, unsigned long long ctr, float p) {
+  unsigned long long z = seed * 0x9E3779B97F4A7C15ull + ctr * 0xD1342543DE82EF95ull;
   z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
   z ^= z >> 27; z *= 0x94D049BB133111EBull;
   z ^= z >> 31;
   const float u = (float)(z >> 40) * (1.0f / 16777216.0f);   // [0,1)
-  mask[idx] = u >= p ? 1 : 0;
+  return u >= p ? 1u : 0u;
+}
+// a thread produces 8 consecutive keep bytes and stores them as one 64-bit word (the byte-per-thread version spent its
+// time in 1-byte stores: 30 us for the 12 MB of masks of a bench step); the value of every element is unchanged
+__device__ __forceinline__ void keep_bytes8(i64 n, float p, unsigned long long seed, unsigned long long base,
+                                            unsigned char* __restrict__ mask) {
+  const i64 i0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i0 >= n) return;
+  if (i0 + 8 <= n && (reinterpret_cast<uintptr_t>(mask) & 7) == 0) {
+    unsigned long long w = 0;
+#pragma unroll
+    for (int e = 0; e < 8; e++) w |= (unsigned long long)keep_byte(seed, base + (unsigned long long)(i0 + e), p) << (8 * e);
+    *reinterpret_cast<unsigned long long*>(mask + i0) = w;
+  } else {
+    for (i64 i = i0; i < n && i < i0 + 8; i++) mask[i] = (unsigned char)keep_byte(seed, base + (unsigned long long)i, p);
+  }
+}
+
+__global__ void dropout_mask_kernel(i64 n, float p, unsigned long long seed, unsigned long long offset,
+                                    unsigned char* __restrict__ mask) {
+  keep_bytes8(n, p, seed, offset, mask);
 }
 
 // Device-resident step state for CUDA-graph replays (nothing that changes from step to step may be a kernel
@@ -261,15 +298,7 @@ __global__ void step_advance_kernel(unsigned long long* state, float beta1, floa
 __global__ void dropout_mask_dev_kernel(i64 n, float p, unsigned long long seed, const unsigned long long* __restrict__ state,
                                         unsigned long long per_step, unsigned long long offset,
                                         unsigned char* __restrict__ mask) {
-  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  const unsigned long long base = offset + state[0] * per_step;
-  unsigned long long z = seed * 0x9E3779B97F4A7C15ull + (base + (unsigned long long)idx) * 0xD1342543DE82EF95ull;
-  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
-  z ^= z >> 27; z *= 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);   // [0,1)
-  mask[idx] = u >= p ? 1 : 0;
+  keep_bytes8(n, p, seed, offset + state[0] * per_step, mask);
 }
 
 __global__ void adam_dev_kernel(i64 n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -335,7 +364,7 @@ extern "C" int mmdfn_head_fwd(int N, int C, const float* F, const unsigned char*
   int sms = 0;
   MMDFN_TRY(head_init(&sms));
   if (((uintptr_t)F | (uintptr_t)R) & 15 || (mask && ((uintptr_t)mask & 3))) return MMDFN_EINVAL;
-  const int grid = min(2 * sms, ceil_div(N, 8));
+  const int grid = min(4 * sms, ceil_div(N, 8));             // one utterance per warp while the CTAs are co-resident
   const size_t smem = (size_t)C * 900 * sizeof(float);
   if (C <= 8) head_fused_fwd_kernel<8><<<grid, 256, smem, st>>>(N, C, F, mask, mask_scale, relu, Wc, bc, R, log_prob);
   else head_fused_fwd_kernel<16><<<grid, 256, smem, st>>>(N, C, F, mask, mask_scale, relu, Wc, bc, R, log_prob);
@@ -362,7 +391,7 @@ extern "C" int mmdfn_head_bwd(int N, int C, const unsigned char* mask, float mas
   if (((uintptr_t)dF | (uintptr_t)R) & 15 || (mask && ((uintptr_t)mask & 3))) return MMDFN_EINVAL;
   int sms = 0;
   MMDFN_TRY(head_init(&sms));
-  const int grid = min(2 * sms, ceil_div(N, 8));
+  const int grid = min(4 * sms, ceil_div(N, 8));
   const size_t smem = (size_t)C * 900 * sizeof(float);
   const dim3 wg(ceil_div(901, 128), ceil_div(N, HW_ROWS));
   if (C <= 8) {
@@ -406,7 +435,7 @@ extern "C" int mmdfn_dropout_mask(long long n, float p, unsigned long long seed,
                                   unsigned char* mask, void* stream) {
   if (!mask) return MMDFN_ENULL;
   if (n <= 0) return 0;
-  dropout_mask_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(n, p, seed, offset, mask);
+  dropout_mask_kernel<<<(unsigned)ceil_div64(n, 2048), 256, 0, (cudaStream_t)stream>>>(n, p, seed, offset, mask);
   MMDFN_LAUNCH_CHECK();
   return 0;
 }
@@ -438,7 +467,7 @@ extern "C" int mmdfn_dropout_mask_dev(long long n, float p, unsigned long long s
                                       void* stream) {
   if (!mask || !state) return MMDFN_ENULL;
   if (n <= 0) return 0;
-  dropout_mask_dev_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(n, p, seed, state, per_step, offset, mask);
+  dropout_mask_dev_kernel<<<(unsigned)ceil_div64(n, 2048), 256, 0, (cudaStream_t)stream>>>(n, p, seed, state, per_step, offset, mask);
   MMDFN_LAUNCH_CHECK();
   return 0;
 }

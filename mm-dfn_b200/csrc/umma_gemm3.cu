@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
       for (int i = 0; i < NPB; i++) {
         if (b_off[i] < 0) continue;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bok[i]) {
+        if (bok[i] && p.dbg != 7) {
           const float* b = bptr[i] + (i64)c * bstep;
           if (B_KMAJ) {
             v = __ldg(reinterpret_cast<const float4*>(b));

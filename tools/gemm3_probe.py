@@ -22,5 +22,5 @@ def timed(ta, tb, M, N, K, variant):
     return e0.elapsed_time(e1) * 1e3 / 20
 for name, ta, tb, M, N, K in (("NT big", 0, 1, 153600, 300, 200), ("NT big K=800", 0, 1, 153600, 300, 800), ("NT gru in-gemm", 0, 1, 19200, 300, 200), ("NT one wave", 0, 1, 18944, 160, 200),
                               ("NT one wave K=800", 0, 1, 18944, 160, 800), ("NT one wave K=16", 0, 1, 18944, 160, 16)):
-    r = {v: timed(ta, tb, M, N, K, v) for v in (3, 31, 32, 33, 34, 2)}
-    print(f"{name:20s} M={M} N={N} K={K}: gen3 {r[3]:7.1f} us | no-MMA {r[31]:7.1f} | BN<=112 {r[32]:7.1f} | BN<=128 {r[33]:7.1f} | BN<=144 {r[34]:7.1f} | gen2 {r[2]:7.1f}", flush=True)
+    r = {v: timed(ta, tb, M, N, K, v) for v in (3, 31, 37, 2)}
+    print(f"{name:20s} M={M} N={N} K={K}: gen3 {r[3]:7.1f} us | no-MMA {r[31]:7.1f} | no B loads {r[37]:7.1f} | gen2 {r[2]:7.1f}", flush=True)
