@@ -5,4 +5,3 @@ for w in c4-ragged c2 c3; do
 done
 timeout 600 python bench.py --steps 20 --warmup 3 --layers 16 --no-cpu-baseline > gpurun_out/r2m_bench_k16.json 2> gpurun_out/r2m_bench_k16.err; echo "bench k16 rc=$?"; cut -c1-230 gpurun_out/r2m_bench_k16.json
 timeout 900 python bench.py --steps 10 --warmup 3 --workload c5 > gpurun_out/r2m_bench_c5.json 2> gpurun_out/r2m_bench_c5.err; echo "bench c5 rc=$?"; cut -c1-230 gpurun_out/r2m_bench_c5.json; tail -3 gpurun_out/r2m_bench_c5.err
-timeout 900 python tools/trainer_bench.py --epochs 4 > gpurun_out/r2m_trainer_bench.json 2> gpurun_out/r2m_trainer_bench.err; echo "trainer rc=$?"; cut -c1-1500 gpurun_out/r2m_trainer_bench.json; tail -3 gpurun_out/r2m_trainer_bench.err
