@@ -484,7 +484,10 @@ int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A
   // for every form whose K-contiguous operands are 16-byte aligned.  mmdfn_gemm_tc_set_variant: 1 = first generation
   // only, 2 = second generation where eligible, 112 / 160 / 224 = first generation with a forced column tile (A/B timing).
   if (g_ug_variant == 0 || g_ug_variant == 3) {
-    if (umma_gemm3_eligible(ta, tb, M, N, K, A, lda, B, ldb)) {
+    // (the very long contractions of the TN form -- weight gradients over all T * nseq slots -- stay on the first
+    // generation by default: measured 36 vs 39 us at 300 x 200 x 19200, 55 vs 61 us at 600 x 200 x 19200)
+    const bool long_tn = ta && K >= 16384 && g_ug_variant == 0;
+    if (!long_tn && umma_gemm3_eligible(ta, tb, M, N, K, A, lda, B, ldb)) {
       const int sp = umma_gemm3_splits(M, N, K, bias == nullptr && act == 0);
       if (sp > 1 && beta != 1.f) {
         ug_scale2d_kernel<<<(unsigned)ceil_div64((i64)M * N, 256), 256, 0, st>>>(C, ldc, M, N, beta);

@@ -1,5 +1,5 @@
 """Standalone check of mmdfn_gemm_tc (tcgen05 3xTF32 GEMM) against fp64, printing the error per shape and mode
-next to the FFMA kernel's; also times both.  Usage (GPU box): python tools/umma_check.py"""
+next to the FFMA kernel's; also times both, the three kernel generations and torch.matmul (cuBLAS) on the same shapes.  Usage (GPU box): python tools/umma_check.py"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -74,15 +74,33 @@ def timed(ta, tb, M, N, K, variant, beta=0.0):
     L.call("mmdfn_gemm_tc_set_variant", 0)
     ref = (A.double().t() if ta else A.double()) @ (B.double().t() if tb else B.double())
     return e0.elapsed_time(e1) * 1e3 / 20
+def cublas(ta, tb, M, N, K, tf32):
+    """torch.matmul on the same operands and layouts (cuBLAS / cuBLASLt), graph-replayed like the kernels above"""
+    A = torch.randn((K, M) if ta else (M, K), device=dev); B = torch.randn((N, K) if tb else (K, N), device=dev); C = torch.zeros(M, N, device=dev)
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    opA = A.t() if ta else A; opB = B.t() if tb else B
+    for _ in range(3):
+        torch.matmul(opA, opB, out=C)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(20):
+            torch.matmul(opA, opB, out=C)
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return e0.elapsed_time(e1) * 1e3 / 20
 for name, ta, tb, M, N, K in (("NT proj audio", 0, 1, 3200, 200, 512), ("NT proj visual", 0, 1, 3200, 200, 1024), ("NT gru in-gemm party", 0, 1, 9600, 600, 200),
                               ("NT gru in-gemm", 0, 1, 19200, 300, 200), ("NT lstm gates", 0, 1, 9600, 400, 100), ("NT big", 0, 1, 153600, 300, 200),
                               ("NN dx", 0, 0, 19200, 200, 300), ("NN dgates W", 0, 0, 9600, 100, 400), ("NN R_all", 0, 0, 9600, 200, 100),
                               ("TN dW_ih splitK", 1, 0, 300, 200, 19200), ("TN dW gates", 1, 0, 400, 100, 9600), ("TN dW proj", 1, 0, 200, 1024, 3200),
                               ("NT proj text", 0, 1, 3200, 200, 100), ("NN dx party l0", 0, 0, 9600, 200, 600), ("TN dW_ih l1 both", 1, 0, 600, 200, 19200)):
     t1, t2, t3 = timed(ta, tb, M, N, K, 1), timed(ta, tb, M, N, K, 2), timed(ta, tb, M, N, K, 3)
+    tc32, tctf = cublas(ta, tb, M, N, K, False), cublas(ta, tb, M, N, K, True)
     gf = 2.0 * M * N * K / 1e9
     print(f"{name:24s} M={M:6d} N={N:4d} K={K:6d}  gen1 {t1:7.1f} us ({gf/t1*1e3:6.1f} TF/s)   gen2 {t2:7.1f} us ({gf/t2*1e3:6.1f} TF/s)   "
-          f"gen3 {t3:7.1f} us ({gf/t3*1e3:6.1f} TF/s)   gen3 vs best x{min(t1, t2)/t3:.2f}", flush=True)
+          f"gen3 {t3:7.1f} us ({gf/t3*1e3:6.1f} TF/s)   gen3 vs best x{min(t1, t2)/t3:.2f}   | torch.matmul fp32 (cuBLAS) {tc32:7.1f} us ({gf/tc32*1e3:6.1f} TF/s), "
+          f"allow_tf32 (1xTF32, NOT fp32-accurate) {tctf:7.1f} us", flush=True)
 for bn in (() if "--quick" in sys.argv else (112, 160, 224)):
     L.call("mmdfn_gemm_tc_set_variant", bn)
     print(f"--- forced BN={bn}")
