@@ -428,8 +428,7 @@ extern "C" int mmdfn_bigru2_fwd(int T, int nseq, long long rows, const float* x,
   float* gates2 = xg2 + slots * 600;
   if (rows > 2000000000LL / 600 || slots > 2000000000LL / 1) return MMDFN_ERANGE;
   // layer 0 input gates for both directions
-  MMDFN_TRY(gemm(false, true, (int)rows, 300, 200, 1.f, x, 200, w[0], 200, 0.f, xg1, 600, w[2], 0, st));
-  MMDFN_TRY(gemm(false, true, (int)rows, 300, 200, 1.f, x, 200, w[4], 200, 0.f, xg1 + 300, 600, w[6], 0, st));
+  MMDFN_TRY(gemm_nt_pair((int)rows, 300, 300, 200, x, 200, w[0], w[4], 200, xg1, 600, w[2], w[6], st));
   GruFwdArgs a{T, nseq, xg1, rowmap, {w[2], w[6]}, {w[1], w[5]}, {w[3], w[7]}, y1, gates1};
   MMDFN_TRY(launch_gru_fwd(a, st));
   const float* l1in = y1;
@@ -437,8 +436,7 @@ extern "C" int mmdfn_bigru2_fwd(int T, int nseq, long long rows, const float* x,
     MMDFN_TRY(mask_mul(y1, mask, mask_scale, slots * 200, y1d, st));
     l1in = y1d;
   }
-  MMDFN_TRY(gemm(false, true, (int)slots, 300, 200, 1.f, l1in, 200, w[8], 200, 0.f, xg2, 600, w[10], 0, st));
-  MMDFN_TRY(gemm(false, true, (int)slots, 300, 200, 1.f, l1in, 200, w[12], 200, 0.f, xg2 + 300, 600, w[14], 0, st));
+  MMDFN_TRY(gemm_nt_pair((int)slots, 300, 300, 200, l1in, 200, w[8], w[12], 200, xg2, 600, w[10], w[14], st));
   GruFwdArgs b{T, nseq, xg2, nullptr, {w[10], w[14]}, {w[9], w[13]}, {w[11], w[15]}, y2, gates2};
   MMDFN_TRY(launch_gru_fwd(b, st));
   return 0;
@@ -504,8 +502,8 @@ extern "C" int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x,
   GruBwdArgs b{T, nseq, dy2, y2, gates2, {w[9], w[13]}, dxg, dgh, {dw[10], dw[14]}, {dw[11], dw[15]}};
   MMDFN_TRY(launch_gru_bwd(b, st));
   MMDFN_TRY(gru_layer_wgrads(T, nseq, slots, dxg, l1in, dgh, y2, dw, 8, wbeta, st));
-  MMDFN_TRY(gemm(false, false, (int)slots, 200, 300, 1.f, dxg, 600, w[8], 200, 0.f, dy1, 200, nullptr, 0, st));
-  MMDFN_TRY(gemm(false, false, (int)slots, 200, 300, 1.f, dxg + 300, 600, w[12], 200, 1.f, dy1, 200, nullptr, 0, st));
+  // d(layer-1 input) = dgates_f W_ih_f + dgates_b W_ih_b: one contraction over the 600 gate columns
+  MMDFN_TRY(gemm_nn_kpair((int)slots, 200, 300, 300, dxg, 600, w[8], w[12], 200, 0.f, dy1, 200, st));
   if (mask) {
     MMDFN_TRY(mask_mul(dy1, mask, mask_scale, slots * 200, dy1, st));
   }
@@ -522,8 +520,7 @@ extern "C" int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x,
   MMDFN_TRY(gru_layer_wgrads(T, nseq, rows, dgate_in, x, dgh, y1, dw, 0, wbeta, st));
   if (dx) {
     const float beta = accumulate_dx ? 1.f : 0.f;
-    MMDFN_TRY(gemm(false, false, (int)rows, 200, 300, 1.f, dgate_in, 600, w[0], 200, beta, dx, 200, nullptr, 0, st));
-    MMDFN_TRY(gemm(false, false, (int)rows, 200, 300, 1.f, dgate_in + 300, 600, w[4], 200, 1.f, dx, 200, nullptr, 0, st));
+    MMDFN_TRY(gemm_nn_kpair((int)rows, 200, 300, 300, dgate_in, 600, w[0], w[4], 200, beta, dx, 200, st));
   }
   return 0;
 }

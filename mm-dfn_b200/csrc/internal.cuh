@@ -22,6 +22,17 @@ void umma_gemm3_set_debug(int v);
 void umma_gemm3_set_stamps(long long* device_buf);
 int umma_gemm3(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64 lda, const float* B, i64 ldb,
                float beta, float* C, i64 ldc, const float* bias, int act, int splits, cudaStream_t st);
+int umma_gemm3_nt_pair(int M, int N1, int N2, int K, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb,
+                       float* C, i64 ldc, const float* bias1, const float* bias2, cudaStream_t st);
+int umma_gemm3_nn_kpair(int M, int N, int K1, int K2, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb,
+                        float beta, float* C, i64 ldc, cudaStream_t st);
+// operand pairs: one launch on the third-generation tensor-core kernel where it applies, two plain gemm() calls otherwise
+//   gemm_nt_pair:   C[:, :N1] = A B1^T + bias1 ; C[:, N1:N1+N2] = A B2^T + bias2
+//   gemm_nn_kpair:  C = A[:, :K1] B1 + A[:, K1:K1+K2] B2 + beta C
+int gemm_nt_pair(int M, int N1, int N2, int K, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb, float* C,
+                 i64 ldc, const float* bias1, const float* bias2, cudaStream_t st);
+int gemm_nn_kpair(int M, int N, int K1, int K2, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb, float beta,
+                  float* C, i64 ldc, cudaStream_t st);
 // out[n] = beta*out[n] + sum_m A[m*lda + n]
 int colsum(int M, int N, const float* A, i64 lda, float beta, float* out, cudaStream_t st);
 int fill_zero(void* p, size_t bytes, cudaStream_t st);

@@ -529,6 +529,26 @@ int umma_gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A
   return dispatch_bn<2>(p, bn, st);
 }
 
+int gemm_nt_pair(int M, int N1, int N2, int K, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb, float* C,
+                 i64 ldc, const float* bias1, const float* bias2, cudaStream_t st) {
+  const bool big = 2.0 * (double)M * (double)(N1 + N2) * (double)K >= 1.8e8;
+  if (big && (g_ug_variant == 0 || g_ug_variant == 3) && M > 0 && N1 > 0 && N2 > 0 && A && B1 && B2 && C &&
+      umma_gemm3_eligible(false, true, M, N1, K, A, lda, B1, ldb) && (reinterpret_cast<uintptr_t>(B2) & 15) == 0)
+    return umma_gemm3_nt_pair(M, N1, N2, K, A, lda, B1, B2, ldb, C, ldc, bias1, bias2, st);
+  MMDFN_TRY(gemm(false, true, M, N1, K, 1.f, A, lda, B1, ldb, 0.f, C, ldc, bias1, 0, st));
+  return gemm(false, true, M, N2, K, 1.f, A, lda, B2, ldb, 0.f, C + N1, ldc, bias2, 0, st);
+}
+
+int gemm_nn_kpair(int M, int N, int K1, int K2, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb, float beta,
+                  float* C, i64 ldc, cudaStream_t st) {
+  const bool big = 2.0 * (double)M * (double)N * (double)(K1 + K2) >= 1.8e8;
+  if (big && (g_ug_variant == 0 || g_ug_variant == 3) && M > 0 && N > 0 && K1 > 0 && K2 > 0 && (K1 & 3) == 0 && A && B1 && B2 && C &&
+      umma_gemm3_eligible(false, false, M, N, K1 + K2, A, lda, B1, ldb))
+    return umma_gemm3_nn_kpair(M, N, K1, K2, A, lda, B1, B2, ldb, beta, C, ldc, st);
+  MMDFN_TRY(gemm(false, false, M, N, K1, 1.f, A, lda, B1, ldb, beta, C, ldc, nullptr, 0, st));
+  return gemm(false, false, M, N, K2, 1.f, A + K1, lda, B2, ldb, 1.f, C, ldc, nullptr, 0, st);
+}
+
 }  // namespace mmdfn
 
 // profiling aid: device buffer of 128 int64 receiving clock64() phase stamps of CTA 0 (nullptr switches it off)

@@ -56,6 +56,11 @@ struct G3Args {
   float alpha, beta;
   int act, splits;
   int bn, ns;                                              // column tile (multiple of 16, <= 192), stages
+  // operand pairs (one launch instead of two): NT form with nsplit > 0: output columns [0, nsplit) come from B (bias),
+  // columns [nsplit, N) from B2 (bias2); NN form with ksplit > 0: contraction rows [0, ksplit) of B, the rest from B2
+  const float* B2;
+  const float* bias2;
+  int nsplit, ksplit;
   int dbg;                                                 // profiling aid: 1 = skip the MMAs (conversion pace only)
   long long* stamps;                                       // profiling aid: clock64 stamps of CTA 0's converter warp 0 (8 per chunk it owns)
 };
@@ -106,8 +111,17 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = p.bn, ns = p.ns;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
-  const int mrows = min(128, p.M - m0), ncols = min(BN, p.N - n0);
+  // column tile: with an NT operand pair the grid's y axis walks the tiles of the first half, then of the second
+  int ty = blockIdx.y, ncap = p.N, cofs = 0;
+  const float* Bsrc = p.B;
+  const float* biasp = p.bias;
+  if (p.nsplit > 0) {
+    const int t1 = (p.nsplit + BN - 1) / BN;
+    if (ty >= t1) { ty -= t1; Bsrc = p.B2; biasp = p.bias2; ncap = p.N - p.nsplit; cofs = p.nsplit; }
+    else ncap = p.nsplit;
+  }
+  const int m0 = blockIdx.x * 128, n0 = ty * BN;             // n0: column within this half's operand
+  const int mrows = min(128, p.M - m0), ncols = min(BN, ncap - n0);
   const int bpart = (BN >> 3) * G3_SBO, stage_bytes = 2 * bpart;
   // K-contiguous A: G3_NP raw panels (1024-byte aligned: swizzle atom), then the B stages
   uint8_t* const raw = smem + ((1024u - (umma::smem_u32(smem) & 1023u)) & 1023u);
@@ -177,7 +191,11 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
     return v;
   };
   const float* Ag = A_KMAJ ? p.A + (i64)m0 * p.lda : p.A + m0;
-  const float* Bg = B_KMAJ ? p.B + (i64)n0 * p.ldb : p.B + n0;
+  const float* Bg = B_KMAJ ? Bsrc + (i64)n0 * p.ldb : Bsrc + n0;
+  // row k of an N-contiguous B (an operand pair along K switches to B2 at ksplit, a multiple of 4)
+  auto brow = [&](int k) -> const float* {
+    return (p.ksplit > 0 && k >= p.ksplit) ? p.B2 + n0 + (i64)(k - p.ksplit) * p.ldb : Bg + (i64)k * p.ldb;
+  };
   // whole-chunk fast path: base pointers of this thread's pieces at k = kb (advanced by 16 k per chunk), validity flags
   const float* aptr = Ag + (i64)kb * p.lda + arow;                       // M-contiguous A only
   const bool aok = arow < mrows;
@@ -186,9 +204,9 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
 #pragma unroll
   for (int i = 0; i < NPB; i++) {
     bok[i] = b_off[i] >= 0 && b_row[i] < ncols;
-    bptr[i] = B_KMAJ ? Bg + (i64)b_row[i] * p.ldb + kb + 4 * b_kq[i] : Bg + (i64)(kb + 4 * b_kq[i]) * p.ldb + b_row[i];
+    bptr[i] = B_KMAJ ? Bg + (i64)b_row[i] * p.ldb + kb + 4 * b_kq[i] : nullptr;
   }
-  const i64 astep = (i64)G3_KC * p.lda, bstep = B_KMAJ ? (i64)G3_KC : (i64)G3_KC * p.ldb;
+  const i64 astep = (i64)G3_KC * p.lda;
   float4 ra[A_KMAJ ? 1 : 4], rb[NPB];
   auto prefetch = [&](int c) {
     if (c >= nchunks) return;
@@ -214,10 +232,10 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
         if (b_off[i] < 0) continue;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bok[i] && p.dbg != 7) {
-          const float* b = bptr[i] + (i64)c * bstep;
           if (B_KMAJ) {
-            v = __ldg(reinterpret_cast<const float4*>(b));
+            v = __ldg(reinterpret_cast<const float4*>(bptr[i] + c * G3_KC));
           } else {
+            const float* b = brow(k0 + 4 * b_kq[i]) + b_row[i];
             v.x = __ldg(b);
             v.y = __ldg(b + p.ldb);
             v.z = __ldg(b + 2 * p.ldb);
@@ -235,7 +253,8 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
 #pragma unroll
     for (int i = 0; i < NPB; i++)
       if (b_off[i] >= 0)
-        rb[i] = B_KMAJ ? ldk(Bg, p.ldb, b_row[i], ncols, k0 + 4 * b_kq[i]) : ldm(Bg, p.ldb, b_row[i], ncols, k0 + 4 * b_kq[i]);
+        rb[i] = B_KMAJ ? ldk(Bg, p.ldb, b_row[i], ncols, k0 + 4 * b_kq[i])
+                       : ldm(brow(k0 + 4 * b_kq[i]) - (i64)(k0 + 4 * b_kq[i]) * p.ldb, p.ldb, b_row[i], ncols, k0 + 4 * b_kq[i]);
   };
   if (warp < G3_CONVW) prefetch(g);
   umma::tc_fence_before_sync();
@@ -371,7 +390,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
 
   // ---- epilogue: 32 x 32 panels, TMEM -> registers -> padded scratch -> lanes along the row ----
   float* scr = reinterpret_cast<float*>(smem + warp * G3_SCRATCH);
-  const bool vec_red = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((n0 & 3) == 0);
+  const bool vec_red = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (((cofs + n0) & 3) == 0);
   const int npanels = (ncols + 31) >> 5;
   for (int pn = g; pn < npanels; pn += 4) {
     const int c0 = 32 * pn;
@@ -397,25 +416,25 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
 #pragma unroll 4
       for (int r4 = 0; r4 < 32; r4 += 4) {
         const int r = r4 + rsub, row = m0 + 32 * q + r;
-        if (row < p.M && n < p.N && c0 + cq < BN) {
-          float* cp = p.C + (i64)row * p.ldc + n;
+        if (row < p.M && n < ncap && c0 + cq < BN) {
+          float* cp = p.C + (i64)row * p.ldc + cofs + n;
           const float* sv = scr + r * 33 + cq;
-          if (vec_red && n + 3 < p.N) {
+          if (vec_red && n + 3 < ncap) {
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(p.alpha * sv[0]), "f"(p.alpha * sv[1]),
                          "f"(p.alpha * sv[2]), "f"(p.alpha * sv[3]) : "memory");
           } else {
 #pragma unroll
             for (int e = 0; e < 4; e++)
-              if (n + e < p.N) atomicAdd(cp + e, p.alpha * sv[e]);
+              if (n + e < ncap) atomicAdd(cp + e, p.alpha * sv[e]);
           }
         }
       }
     } else {
       const int n = n0 + c0 + lane;
-      const bool cok = (c0 + lane < BN) && n < p.N;
-      const float bv = (cok && p.bias) ? p.bias[n] : 0.f;
+      const bool cok = (c0 + lane < BN) && n < ncap;
+      const float bv = (cok && biasp) ? biasp[n] : 0.f;
       const int rmax = min(32, p.M - (m0 + 32 * q));
-      float* cp = p.C + (i64)(m0 + 32 * q) * p.ldc + n;
+      float* cp = p.C + (i64)(m0 + 32 * q) * p.ldc + cofs + n;
       if (cok) {
         if (p.beta != 0.f) {
 #pragma unroll 8
@@ -491,7 +510,8 @@ static int launch_g3(const G3Args& p, cudaStream_t st) {
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return MMDFN_EINVAL;
   }
-  dim3 grid(ceil_div(p.M, 128), ceil_div(p.N, p.bn), p.splits > 1 ? p.splits : 1);
+  const int ytiles = p.nsplit > 0 ? ceil_div(p.nsplit, p.bn) + ceil_div(p.N - p.nsplit, p.bn) : ceil_div(p.N, p.bn);
+  dim3 grid(ceil_div(p.M, 128), ytiles, p.splits > 1 ? p.splits : 1);
   umma_gemm3_kernel<MODE><<<grid, G3_THREADS, smem, st>>>(tm, p);
   MMDFN_LAUNCH_CHECK();
   return 0;
@@ -520,7 +540,7 @@ int umma_gemm3_splits(int M, int N, int K, bool plain_epilogue) {
 
 int umma_gemm3(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64 lda, const float* B, i64 ldb,
                float beta, float* C, i64 ldc, const float* bias, int act, int splits, cudaStream_t st) {
-  G3Args p{A, lda, B, ldb, C, ldc, bias, M, N, K, alpha, beta, act, splits, 0, 0, g_g3_dbg, g_g3_stamps};
+  G3Args p{A, lda, B, ldb, C, ldc, bias, M, N, K, alpha, beta, act, splits, 0, 0, nullptr, nullptr, 0, 0, g_g3_dbg, g_g3_stamps};
   p.bn = g3_pick_bn(N);
   p.ns = (512 - 2 * p.bn) / 32;
   if (p.ns > G3_NS_MAX) p.ns = G3_NS_MAX;
@@ -528,6 +548,30 @@ int umma_gemm3(bool ta, bool tb, int M, int N, int K, float alpha, const float* 
   if (!ta && tb) return launch_g3<0>(p, st);
   if (!ta && !tb) return launch_g3<1>(p, st);
   return launch_g3<2>(p, st);
+}
+
+// C[:, :N1] = A B1^T + bias1 and C[:, N1:N1+N2] = A B2^T + bias2 in ONE launch (the two directions' input-gate products
+// of a GRU layer: same A, two (300, 200) weights).  Caller checked umma_gemm3_eligible for (A, B1) and B2's alignment.
+int umma_gemm3_nt_pair(int M, int N1, int N2, int K, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb,
+                       float* C, i64 ldc, const float* bias1, const float* bias2, cudaStream_t st) {
+  G3Args p{A, lda, B1, ldb, C, ldc, bias1, M, N1 + N2, K, 1.f, 0.f, 0, 1, 0, 0, B2, bias2, N1, 0, g_g3_dbg, g_g3_stamps};
+  p.bn = g3_pick_bn(N1 > N2 ? N1 : N2);
+  p.ns = (512 - 2 * p.bn) / 32;
+  if (p.ns > G3_NS_MAX) p.ns = G3_NS_MAX;
+  while (p.ns > 2 && p.ns * 2 * (p.bn / 8) * G3_SBO + G3_NP * G3_PANEL + 1024 > 226 * 1024) p.ns--;
+  return launch_g3<0>(p, st);
+}
+
+// C = A[:, :K1] B1 + A[:, K1:K1+K2] B2 (+ beta C) in ONE launch, B1 (K1, N) and B2 (K2, N) row-major with the same row
+// stride (the input gradient of a bidirectional layer: dx = dgates_f W_f + dgates_b W_b).  K1 must be a multiple of 4.
+int umma_gemm3_nn_kpair(int M, int N, int K1, int K2, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb,
+                        float beta, float* C, i64 ldc, cudaStream_t st) {
+  G3Args p{A, lda, B1, ldb, C, ldc, nullptr, M, N, K1 + K2, 1.f, beta, 0, 1, 0, 0, B2, nullptr, 0, K1, g_g3_dbg, g_g3_stamps};
+  p.bn = g3_pick_bn(N);
+  p.ns = (512 - 2 * p.bn) / 32;
+  if (p.ns > G3_NS_MAX) p.ns = G3_NS_MAX;
+  while (p.ns > 2 && p.ns * 2 * (p.bn / 8) * G3_SBO + G3_NP * G3_PANEL + 1024 > 226 * 1024) p.ns--;
+  return launch_g3<1>(p, st);
 }
 
 }  // namespace mmdfn
