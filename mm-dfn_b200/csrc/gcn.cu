@@ -320,14 +320,15 @@ extern "C" int mmdfn_gcn_stack_bwd(int B, int N, int Lmax, const int* dia_off, c
     lstm_bwd_kernel<<<nblk(n3 * GG), 256, 0, st>>>(n3, dh, have_carry ? dcc : nullptr, gates, c, cprev, dgates, dcc);
     MMDFN_LAUNCH_CHECK();
     // dz_l = dz_{l+1} (residual +q) + dgates W_ih ; dhc = dgates W_hh
-    MMDFN_TRY(gemm(false, false, (int)n3, GG, 4 * GG, 1.f, dgates, 4 * GG, w_ih, GG, 1.f, dz, GG, nullptr, 0, st));
-    if (l > 0) MMDFN_TRY(gemm(false, false, (int)n3, GG, 4 * GG, 1.f, dgates, 4 * GG, w_hh, GG, 0.f, dhc, GG, nullptr, 0, st));
     const float beta = (first_rnn && !grads_zeroed) ? 0.f : 1.f;
-    MMDFN_TRY(gemm(true, false, 4 * GG, GG, (int)n3, 1.f, dgates, 4 * GG, zprev, GG, beta, dw_ih, GG, nullptr, 0, st));
     if (l > 0) {
-      MMDFN_TRY(gemm(true, false, 4 * GG, GG, (int)n3, 1.f, dgates, 4 * GG, hprev, GG, beta, dw_hh, GG, nullptr, 0, st));
-    } else if (beta == 0.f) {
-      MMDFN_TRY(fill_zero(dw_hh, (size_t)4 * GG * GG * sizeof(float), st));      // h_{-1} = 0: no contribution from layer 0
+      // input and recurrent halves share dgates: one launch each for the two data gradients and the two weight gradients
+      MMDFN_TRY(gemm_npair(false, (int)n3, GG, 4 * GG, dgates, 4 * GG, w_ih, w_hh, GG, 1.f, dz, 0.f, dhc, GG, st));
+      MMDFN_TRY(gemm_npair(true, 4 * GG, GG, (int)n3, dgates, 4 * GG, zprev, hprev, GG, beta, dw_ih, beta, dw_hh, GG, st));
+    } else {
+      MMDFN_TRY(gemm(false, false, (int)n3, GG, 4 * GG, 1.f, dgates, 4 * GG, w_ih, GG, 1.f, dz, GG, nullptr, 0, st));
+      MMDFN_TRY(gemm(true, false, 4 * GG, GG, (int)n3, 1.f, dgates, 4 * GG, zprev, GG, beta, dw_ih, GG, nullptr, 0, st));
+      if (beta == 0.f) MMDFN_TRY(fill_zero(dw_hh, (size_t)4 * GG * GG * sizeof(float), st));      // h_{-1} = 0: no contribution from layer 0
     }
     MMDFN_TRY(colsum((int)n3, 4 * GG, dgates, 4 * GG, beta, db_ih, st));
     first_rnn = false;

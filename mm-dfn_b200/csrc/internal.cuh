@@ -26,6 +26,11 @@ int umma_gemm3_nt_pair(int M, int N1, int N2, int K, const float* A, i64 lda, co
                        float* C, i64 ldc, const float* bias1, const float* bias2, cudaStream_t st);
 int umma_gemm3_nn_kpair(int M, int N, int K1, int K2, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb,
                         float beta, float* C, i64 ldc, cudaStream_t st);
+int umma_gemm3_npair(bool ta, int M, int N, int K, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb,
+                     float beta1, float* C1, float beta2, float* C2, i64 ldc, int splits, cudaStream_t st);
+//   gemm_npair:     C1 = op(A) B1 + beta1 C1 ; C2 = op(A) B2 + beta2 C2   (NN or TN form, N columns each)
+int gemm_npair(bool ta, int M, int N, int K, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb, float beta1,
+               float* C1, float beta2, float* C2, i64 ldc, cudaStream_t st);
 // operand pairs: one launch on the third-generation tensor-core kernel where it applies, two plain gemm() calls otherwise
 //   gemm_nt_pair:   C[:, :N1] = A B1^T + bias1 ; C[:, N1:N1+N2] = A B2^T + bias2
 //   gemm_nn_kpair:  C = A[:, :K1] B1 + A[:, K1:K1+K2] B2 + beta C

@@ -539,6 +539,23 @@ int gemm_nt_pair(int M, int N1, int N2, int K, const float* A, i64 lda, const fl
   return gemm(false, true, M, N2, K, 1.f, A, lda, B2, ldb, 0.f, C + N1, ldc, bias2, 0, st);
 }
 
+int gemm_npair(bool ta, int M, int N, int K, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb, float beta1,
+               float* C1, float beta2, float* C2, i64 ldc, cudaStream_t st) {
+  const bool big = 2.0 * (double)M * (double)(2 * N) * (double)K >= 1.8e8;
+  const bool long_tn = ta && K >= 16384;
+  if (big && !long_tn && (g_ug_variant == 0 || g_ug_variant == 3) && M > 0 && N > 0 && K > 0 && A && B1 && B2 && C1 && C2 &&
+      umma_gemm3_eligible(ta, false, M, N, K, A, lda, B1, ldb)) {
+    const int sp = umma_gemm3_splits(M, 2 * N, K, true);
+    if (sp > 1) {
+      if (beta1 != 1.f) { ug_scale2d_kernel<<<(unsigned)ceil_div64((i64)M * N, 256), 256, 0, st>>>(C1, ldc, M, N, beta1); MMDFN_LAUNCH_CHECK(); }
+      if (beta2 != 1.f) { ug_scale2d_kernel<<<(unsigned)ceil_div64((i64)M * N, 256), 256, 0, st>>>(C2, ldc, M, N, beta2); MMDFN_LAUNCH_CHECK(); }
+    }
+    return umma_gemm3_npair(ta, M, N, K, A, lda, B1, B2, ldb, beta1, C1, beta2, C2, ldc, sp, st);
+  }
+  MMDFN_TRY(gemm(ta, false, M, N, K, 1.f, A, lda, B1, ldb, beta1, C1, ldc, nullptr, 0, st));
+  return gemm(ta, false, M, N, K, 1.f, A, lda, B2, ldb, beta2, C2, ldc, nullptr, 0, st);
+}
+
 int gemm_nn_kpair(int M, int N, int K1, int K2, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb, float beta,
                   float* C, i64 ldc, cudaStream_t st) {
   const bool big = 2.0 * (double)M * (double)N * (double)(K1 + K2) >= 1.8e8;

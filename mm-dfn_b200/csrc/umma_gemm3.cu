@@ -60,6 +60,8 @@ struct G3Args {
   // columns [nsplit, N) from B2 (bias2); NN form with ksplit > 0: contraction rows [0, ksplit) of B, the rest from B2
   const float* B2;
   const float* bias2;
+  float* C2;                                               // column pair: where the second half's columns go (its column 0), with beta2
+  float beta2;
   int nsplit, ksplit;
   int dbg;                                                 // profiling aid: 1 = skip the MMAs (conversion pace only)
   long long* stamps;                                       // profiling aid: clock64 stamps of CTA 0's converter warp 0 (8 per chunk it owns)
@@ -112,12 +114,14 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = p.bn, ns = p.ns;
   // column tile: with an NT operand pair the grid's y axis walks the tiles of the first half, then of the second
-  int ty = blockIdx.y, ncap = p.N, cofs = 0;
+  int ty = blockIdx.y, ncap = p.N;
   const float* Bsrc = p.B;
   const float* biasp = p.bias;
+  float* Cdst = p.C;
+  float beta = p.beta;
   if (p.nsplit > 0) {
     const int t1 = (p.nsplit + BN - 1) / BN;
-    if (ty >= t1) { ty -= t1; Bsrc = p.B2; biasp = p.bias2; ncap = p.N - p.nsplit; cofs = p.nsplit; }
+    if (ty >= t1) { ty -= t1; Bsrc = p.B2; biasp = p.bias2; ncap = p.N - p.nsplit; Cdst = p.C2; beta = p.beta2; }
     else ncap = p.nsplit;
   }
   const int m0 = blockIdx.x * 128, n0 = ty * BN;             // n0: column within this half's operand
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
 
   // ---- epilogue: 32 x 32 panels, TMEM -> registers -> padded scratch -> lanes along the row ----
   float* scr = reinterpret_cast<float*>(smem + warp * G3_SCRATCH);
-  const bool vec_red = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (((cofs + n0) & 3) == 0);
+  const bool vec_red = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cdst) & 15) == 0) && ((n0 & 3) == 0);
   const int npanels = (ncols + 31) >> 5;
   for (int pn = g; pn < npanels; pn += 4) {
     const int c0 = 32 * pn;
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
       for (int r4 = 0; r4 < 32; r4 += 4) {
         const int r = r4 + rsub, row = m0 + 32 * q + r;
         if (row < p.M && n < ncap && c0 + cq < BN) {
-          float* cp = p.C + (i64)row * p.ldc + cofs + n;
+          float* cp = Cdst + (i64)row * p.ldc + n;
           const float* sv = scr + r * 33 + cq;
           if (vec_red && n + 3 < ncap) {
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(p.alpha * sv[0]), "f"(p.alpha * sv[1]),
@@ -434,12 +438,12 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
       const bool cok = (c0 + lane < BN) && n < ncap;
       const float bv = (cok && biasp) ? biasp[n] : 0.f;
       const int rmax = min(32, p.M - (m0 + 32 * q));
-      float* cp = p.C + (i64)(m0 + 32 * q) * p.ldc + cofs + n;
+      float* cp = Cdst + (i64)(m0 + 32 * q) * p.ldc + n;
       if (cok) {
-        if (p.beta != 0.f) {
+        if (beta != 0.f) {
 #pragma unroll 8
           for (int r = 0; r < rmax; r++) {
-            float t = fmaf(p.beta, cp[(i64)r * p.ldc], p.alpha * scr[r * 33 + lane]) + bv;
+            float t = fmaf(beta, cp[(i64)r * p.ldc], p.alpha * scr[r * 33 + lane]) + bv;
             if (p.act == 1) t = fmaxf(t, 0.f);
             cp[(i64)r * p.ldc] = t;
           }
@@ -540,7 +544,7 @@ int umma_gemm3_splits(int M, int N, int K, bool plain_epilogue) {
 
 int umma_gemm3(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64 lda, const float* B, i64 ldb,
                float beta, float* C, i64 ldc, const float* bias, int act, int splits, cudaStream_t st) {
-  G3Args p{A, lda, B, ldb, C, ldc, bias, M, N, K, alpha, beta, act, splits, 0, 0, nullptr, nullptr, 0, 0, g_g3_dbg, g_g3_stamps};
+  G3Args p{A, lda, B, ldb, C, ldc, bias, M, N, K, alpha, beta, act, splits, 0, 0, nullptr, nullptr, nullptr, 0.f, 0, 0, g_g3_dbg, g_g3_stamps};
   p.bn = g3_pick_bn(N);
   p.ns = (512 - 2 * p.bn) / 32;
   if (p.ns > G3_NS_MAX) p.ns = G3_NS_MAX;
@@ -554,7 +558,7 @@ int umma_gemm3(bool ta, bool tb, int M, int N, int K, float alpha, const float* 
 // of a GRU layer: same A, two (300, 200) weights).  Caller checked umma_gemm3_eligible for (A, B1) and B2's alignment.
 int umma_gemm3_nt_pair(int M, int N1, int N2, int K, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb,
                        float* C, i64 ldc, const float* bias1, const float* bias2, cudaStream_t st) {
-  G3Args p{A, lda, B1, ldb, C, ldc, bias1, M, N1 + N2, K, 1.f, 0.f, 0, 1, 0, 0, B2, bias2, N1, 0, g_g3_dbg, g_g3_stamps};
+  G3Args p{A, lda, B1, ldb, C, ldc, bias1, M, N1 + N2, K, 1.f, 0.f, 0, 1, 0, 0, B2, bias2, C + N1, 0.f, N1, 0, g_g3_dbg, g_g3_stamps};
   p.bn = g3_pick_bn(N1 > N2 ? N1 : N2);
   p.ns = (512 - 2 * p.bn) / 32;
   if (p.ns > G3_NS_MAX) p.ns = G3_NS_MAX;
@@ -562,11 +566,25 @@ int umma_gemm3_nt_pair(int M, int N1, int N2, int K, const float* A, i64 lda, co
   return launch_g3<0>(p, st);
 }
 
+// C1 = op(A) B1 + beta1 C1 and C2 = op(A) B2 + beta2 C2 in ONE launch for the NN (ta = false) and TN (ta = true) forms: the
+// same A against two N-contiguous operands of N columns each, two separate outputs with the same row stride (the LSTM
+// gate's input / recurrent gradients and weight gradients of a graph layer).  `splits` as from umma_gemm3_splits for
+// (M, 2 N, K); outputs pre-scaled by the caller when splits > 1.
+int umma_gemm3_npair(bool ta, int M, int N, int K, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb,
+                     float beta1, float* C1, float beta2, float* C2, i64 ldc, int splits, cudaStream_t st) {
+  G3Args p{A, lda, B1, ldb, C1, ldc, nullptr, M, 2 * N, K, 1.f, beta1, 0, splits, 0, 0, B2, nullptr, C2, beta2, N, 0, g_g3_dbg, g_g3_stamps};
+  p.bn = g3_pick_bn(N);
+  p.ns = (512 - 2 * p.bn) / 32;
+  if (p.ns > G3_NS_MAX) p.ns = G3_NS_MAX;
+  while (p.ns > 2 && p.ns * 2 * (p.bn / 8) * G3_SBO + (ta ? 0 : G3_NP * G3_PANEL + 1024) > 226 * 1024) p.ns--;
+  return ta ? launch_g3<2>(p, st) : launch_g3<1>(p, st);
+}
+
 // C = A[:, :K1] B1 + A[:, K1:K1+K2] B2 (+ beta C) in ONE launch, B1 (K1, N) and B2 (K2, N) row-major with the same row
 // stride (the input gradient of a bidirectional layer: dx = dgates_f W_f + dgates_b W_b).  K1 must be a multiple of 4.
 int umma_gemm3_nn_kpair(int M, int N, int K1, int K2, const float* A, i64 lda, const float* B1, const float* B2, i64 ldb,
                         float beta, float* C, i64 ldc, cudaStream_t st) {
-  G3Args p{A, lda, B1, ldb, C, ldc, nullptr, M, N, K1 + K2, 1.f, beta, 0, 1, 0, 0, B2, nullptr, 0, K1, g_g3_dbg, g_g3_stamps};
+  G3Args p{A, lda, B1, ldb, C, ldc, nullptr, M, N, K1 + K2, 1.f, beta, 0, 1, 0, 0, B2, nullptr, nullptr, 0.f, 0, K1, g_g3_dbg, g_g3_stamps};
   p.bn = g3_pick_bn(N);
   p.ns = (512 - 2 * p.bn) / 32;
   if (p.ns > G3_NS_MAX) p.ns = G3_NS_MAX;

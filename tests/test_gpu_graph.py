@@ -43,6 +43,7 @@ def test_graph_replays_match_eager_steps():
     dev = torch.device("cuda", 0)
     mm, model_e, batches = _build(dev, 0.0)
     tr_e = _trainer(mm, model_e)
+    p_init = tr_e.flat_p.clone()
     eager = []
     for k in range(6):
         t, a, v, q, u, lab = batches[k % 3]
@@ -61,8 +62,14 @@ def test_graph_replays_match_eager_steps():
     assert int(tr_g._state[0]) == 6                                         # device-side step index
     for le, lg in zip(eager, graph):
         assert abs(le - lg) < 2e-5, (eager, graph)
-    # same Adam trajectory (split-K atomics make the two runs differ in the last bits only)
-    assert float((tr_g.flat_p - p_eager).abs().max()) < 5e-5
+    # Same Adam trajectory.  The two runs differ in the last bits of every gradient (split-K / bias atomics), and Adam's
+    # first steps move a parameter by ~lr * sign(g): an element whose gradient is at the noise level may flip, so a max-abs
+    # bound over 1.2 M parameters is a coin toss (seen failing once at 3.4e-4 on an unchanged build).  A wrong step index
+    # or bias correction would shift EVERY update by tens of percent: bound the relative distance of the whole update and
+    # the fraction of elements that moved differently.
+    d_e, d_g = p_eager - p_init, tr_g.flat_p - p_init
+    assert float((d_g - d_e).norm() / d_e.norm()) < 2e-3
+    assert float(((d_g - d_e).abs() > 5e-5).float().mean()) < 1e-4
 
 
 def test_graph_replays_draw_fresh_dropout_masks():
