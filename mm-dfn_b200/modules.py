@@ -491,7 +491,12 @@ class DialogueGNNModel(nn.Module):
         side = _side_stream(dev) if self.use_crn_speaker else None
         tile_l, tile_p = ops.plan_gru_tiles(T, B, 3 * B * S) if side is not None else (0, 0)
         if side is not None:
-            side.wait_stream(main)
+            # the text encoder needs only the text slice of the table (and the masks drawn before it): it starts as soon as
+            # that projection is done, while the audio / visual projections and the speaker partition run on the main stream
+            if ops.Proj3Fn.text_ready is not None:
+                side.wait_event(ops.Proj3Fn.text_ready)
+            else:
+                side.wait_stream(main)
             with torch.cuda.stream(side), ops.gru_tile(tile_l), ops.sink_key("gru_l"):
                 E_l = ops.BiGRU2Fn.apply(Utab[2].reshape(T * B, 200), None, T, B, m_l, scale, *self._gru_weights(self.lstm_l))
         else:

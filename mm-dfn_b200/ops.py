@@ -274,6 +274,7 @@ class GatedFuseFn(torch.autograd.Function):
 
 class Proj3Fn(torch.autograd.Function):
     """U (3,T,B,200) = stack over (a, v, l) of x_m W_m^T + b_m   (code/model.py:1065,1094,1129)."""
+    text_ready = None          # event recorded after the text slice U[2] of the most recent forward was enqueued
 
     @staticmethod
     def forward(ctx, xa, xv, xl, wa, ba, wv, bv, wl, bl):
@@ -284,10 +285,15 @@ class Proj3Fn(torch.autograd.Function):
         rows = T * B
         U = _empty((3, T, B, 200), xa.device)
         st = stream()
-        for m in range(3):
+        # the text projection first: the text encoder (the longer of the two concurrent encoder chains) depends on it alone
+        # and may start on its side stream while the audio / visual projections still run (event: Proj3Fn.text_ready)
+        for m in (2, 0, 1):
             K = xs[m].shape[2]
             call("mmdfn_gemm", 0, 1, rows, 200, K, 1.0, ptr(xs[m]), K, ptr(ws[m]), K, 0.0,
                  U.data_ptr() + m * rows * 200 * 4, 200, ptr(bs[m]), 0, st)
+            if m == 2:
+                Proj3Fn.text_ready = torch.cuda.Event()
+                Proj3Fn.text_ready.record(torch.cuda.current_stream(xa.device))
         ctx.save_for_backward(*xs, *ws)
         ctx.sink_key = _SINK_KEY[0]
         return U
