@@ -90,6 +90,16 @@ int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x, const int*
                      const unsigned char* mask, float mask_scale, const float* y2, const float* dy2,
                      const float* ws_fwd, float* dx, int accumulate_dx, float* const* dw, int dw_zeroed, float* ws,
                      void* stream);
+/* the same encoder with a layer-0 input width other than 200 (x: (rows, in_dim), weight_ih_l0[_reverse]: (300, in_dim),
+   dx: (rows, in_dim)): the text-only configuration's `lstm` = nn.GRU(hidden_, D_e, 2, bidirectional) with
+   hidden_ in {100, 150, 250} (code/model.py:836-849, 1035-1036).  Workspace sizes as for the 200-wide form. */
+int mmdfn_bigru2_fwd_in(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                        const float* const* w, const unsigned char* mask, float mask_scale, float* y2, float* ws,
+                        void* stream);
+int mmdfn_bigru2_bwd_in(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                        const float* const* w, const unsigned char* mask, float mask_scale, const float* y2,
+                        const float* dy2, const float* ws_fwd, float* dx, int accumulate_dx, float* const* dw,
+                        int dw_zeroed, float* ws, void* stream);
 
 /* ---- k3/k4: speaker-party partition + fused scatter/combine/ragged pack ------------------------
  * code/model.py:1070-1090, 1101-1121, 1134-1154 and simple_batch_graphify :553-565.
@@ -276,6 +286,18 @@ int mmdfn_window_sum(int N, int G, int reach_back, int reach_fwd, const int* dia
                      const float* h, float* out, int accumulate, void* stream);
 /* out[b][c][r] = in[b][r][c] */
 int mmdfn_transpose_batched(int batch, int rows, int cols, const float* in, float* out, void* stream);
+
+/* ---- k13 (☆ SURVEY 8f rank 3): nodal attention of the relation path's classifier head ---------------------------
+ * Replaces attentive_node_features + MatchingAttention('general2') (code/model.py:614-645, 66-76) on the ragged node
+ * rows: per dialogue b (rows dia_off[b]..dia_off[b+1]-1 of E, Q, O: (N, D), D <= 512)
+ *     S = tanh(Q_b E_b^T), P = softmax_rows(S), O_b = P E_b          with Q = E W^T + bias (mmdfn_gemm, by the caller).
+ * P, S, dA: sum_b L_b^2 floats, block b row-major at sq_off[b]; row_dia (N): dialogue index of every row.
+ * _bwd overwrites dQ = dA E and dE = P^T dO + dA^T Q (the caller adds dQ W and forms dW = dQ^T E, db = colsum dQ). */
+int mmdfn_nodal_attn_fwd(int B, int N, int D, int Lmax, const int* dia_off, const long long* sq_off, const int* row_dia,
+                         const float* E, const float* Q, float* P, float* S, float* O, void* stream);
+int mmdfn_nodal_attn_bwd(int B, int N, int D, int Lmax, const int* dia_off, const long long* sq_off, const int* row_dia,
+                         const float* E, const float* Q, const float* P, const float* S, const float* dO, float* dA,
+                         float* dQ, float* dE, void* stream);
 
 /* ---- a13: MMGatedAttention 'general' (code/model.py:757-781) -------------------------------------
  * h_m = tanh(P_m), P_m = W_m x_m + b_m (computed by the caller with mmdfn_gemm); z_mn = sigmoid(w_mn.[x_m, x_n, x_m*x_n]

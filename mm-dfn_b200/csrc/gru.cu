@@ -414,8 +414,14 @@ extern "C" long long mmdfn_bigru2_ws_floats(int T, int nseq, long long rows) {
 extern "C" int mmdfn_bigru2_fwd(int T, int nseq, long long rows, const float* x, const int* rowmap,
                                 const float* const* w, const unsigned char* mask, float mask_scale, float* y2,
                                 float* ws, void* stream) {
+  return mmdfn_bigru2_fwd_in(200, T, nseq, rows, x, rowmap, w, mask, mask_scale, y2, ws, stream);
+}
+
+extern "C" int mmdfn_bigru2_fwd_in(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                                   const float* const* w, const unsigned char* mask, float mask_scale, float* y2,
+                                   float* ws, void* stream) {
   if (!x || !w || !y2 || !ws) return MMDFN_ENULL;
-  if (T < 0 || nseq < 0 || rows < 0) return MMDFN_EINVAL;
+  if (T < 0 || nseq < 0 || rows < 0 || in_dim <= 0) return MMDFN_EINVAL;
   if (!rowmap && rows != (i64)T * nseq) return MMDFN_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const i64 slots = (i64)T * nseq;
@@ -428,7 +434,7 @@ extern "C" int mmdfn_bigru2_fwd(int T, int nseq, long long rows, const float* x,
   float* gates2 = xg2 + slots * 600;
   if (rows > 2000000000LL / 600 || slots > 2000000000LL / 1) return MMDFN_ERANGE;
   // layer 0 input gates for both directions
-  MMDFN_TRY(gemm_nt_pair((int)rows, 300, 300, 200, x, 200, w[0], w[4], 200, xg1, 600, w[2], w[6], st));
+  MMDFN_TRY(gemm_nt_pair((int)rows, 300, 300, in_dim, x, in_dim, w[0], w[4], in_dim, xg1, 600, w[2], w[6], st));
   GruFwdArgs a{T, nseq, xg1, rowmap, {w[2], w[6]}, {w[1], w[5]}, {w[3], w[7]}, y1, gates1};
   MMDFN_TRY(launch_gru_fwd(a, st));
   const float* l1in = y1;
@@ -451,17 +457,17 @@ extern "C" long long mmdfn_bigru2_bwd_ws_floats(int T, int nseq, long long rows)
 // One layer's weight gradients.  dgate_in: (in_rows, 600) gradient w.r.t. the input gates of the rows of `xin`
 // (ld 200); dgh: (T*nseq, 600); yl: that layer's output (T, nseq, 200).  Bias gradients were accumulated by the
 // recurrence kernel.  beta = 1 when the caller pre-zeroed the gradient buffers (no zero-init launches).
-static int gru_layer_wgrads(int T, int nseq, i64 in_rows, const float* dgate_in, const float* xin, const float* dgh,
+static int gru_layer_wgrads(int T, int nseq, i64 in_rows, const float* dgate_in, const float* xin, int in_dim, const float* dgh,
                             const float* yl, float* const* dw, int base, float beta, cudaStream_t st) {
   const i64 mprev = (i64)(T - 1) * nseq;
   float* dW_ih_f = dw[base + 0];
   float* dW_ih_b = dw[base + 4];
-  if (dW_ih_b == dW_ih_f + 300 * 200) {
-    // both directions in one GEMM: [dW_ih_f; dW_ih_b] (600,200) = dgate_in^T xin
-    MMDFN_TRY(gemm(true, false, 600, 200, (int)in_rows, 1.f, dgate_in, 600, xin, 200, beta, dW_ih_f, 200, nullptr, 0, st));
+  if (dW_ih_b == dW_ih_f + 300 * in_dim) {
+    // both directions in one GEMM: [dW_ih_f; dW_ih_b] (600, in_dim) = dgate_in^T xin
+    MMDFN_TRY(gemm(true, false, 600, in_dim, (int)in_rows, 1.f, dgate_in, 600, xin, in_dim, beta, dW_ih_f, in_dim, nullptr, 0, st));
   } else {
-    MMDFN_TRY(gemm(true, false, 300, 200, (int)in_rows, 1.f, dgate_in, 600, xin, 200, beta, dW_ih_f, 200, nullptr, 0, st));
-    MMDFN_TRY(gemm(true, false, 300, 200, (int)in_rows, 1.f, dgate_in + 300, 600, xin, 200, beta, dW_ih_b, 200, nullptr, 0, st));
+    MMDFN_TRY(gemm(true, false, 300, in_dim, (int)in_rows, 1.f, dgate_in, 600, xin, in_dim, beta, dW_ih_f, in_dim, nullptr, 0, st));
+    MMDFN_TRY(gemm(true, false, 300, in_dim, (int)in_rows, 1.f, dgate_in + 300, 600, xin, in_dim, beta, dW_ih_b, in_dim, nullptr, 0, st));
   }
   for (int d = 0; d < 2; d++) {
     float* dW_hh = dw[base + 4 * d + 1];
@@ -477,7 +483,16 @@ extern "C" int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x,
                                 const float* const* w, const unsigned char* mask, float mask_scale, const float* y2,
                                 const float* dy2, const float* ws_fwd, float* dx, int accumulate_dx,
                                 float* const* dw, int dw_zeroed, float* ws, void* stream) {
+  return mmdfn_bigru2_bwd_in(200, T, nseq, rows, x, rowmap, w, mask, mask_scale, y2, dy2, ws_fwd, dx, accumulate_dx, dw, dw_zeroed,
+                             ws, stream);
+}
+
+extern "C" int mmdfn_bigru2_bwd_in(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                                   const float* const* w, const unsigned char* mask, float mask_scale, const float* y2,
+                                   const float* dy2, const float* ws_fwd, float* dx, int accumulate_dx,
+                                   float* const* dw, int dw_zeroed, float* ws, void* stream) {
   if (!x || !w || !y2 || !dy2 || !ws_fwd || !dw || !ws) return MMDFN_ENULL;
+  if (in_dim <= 0) return MMDFN_EINVAL;
   if (!rowmap && rows != (i64)T * nseq) return MMDFN_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const i64 slots = (i64)T * nseq;
@@ -501,7 +516,7 @@ extern "C" int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x,
   // ---- layer 1 ----
   GruBwdArgs b{T, nseq, dy2, y2, gates2, {w[9], w[13]}, dxg, dgh, {dw[10], dw[14]}, {dw[11], dw[15]}};
   MMDFN_TRY(launch_gru_bwd(b, st));
-  MMDFN_TRY(gru_layer_wgrads(T, nseq, slots, dxg, l1in, dgh, y2, dw, 8, wbeta, st));
+  MMDFN_TRY(gru_layer_wgrads(T, nseq, slots, dxg, l1in, 200, dgh, y2, dw, 8, wbeta, st));
   // d(layer-1 input) = dgates_f W_ih_f + dgates_b W_ih_b: one contraction over the 600 gate columns
   MMDFN_TRY(gemm_nn_kpair((int)slots, 200, 300, 300, dxg, 600, w[8], w[12], 200, 0.f, dy1, 200, st));
   if (mask) {
@@ -517,10 +532,10 @@ extern "C" int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x,
     MMDFN_LAUNCH_CHECK();
     dgate_in = dG;
   }
-  MMDFN_TRY(gru_layer_wgrads(T, nseq, rows, dgate_in, x, dgh, y1, dw, 0, wbeta, st));
+  MMDFN_TRY(gru_layer_wgrads(T, nseq, rows, dgate_in, x, in_dim, dgh, y1, dw, 0, wbeta, st));
   if (dx) {
     const float beta = accumulate_dx ? 1.f : 0.f;
-    MMDFN_TRY(gemm_nn_kpair((int)rows, 200, 300, 300, dgate_in, 600, w[0], w[4], 200, beta, dx, 200, st));
+    MMDFN_TRY(gemm_nn_kpair((int)rows, in_dim, 300, 300, dgate_in, 600, w[0], w[4], in_dim, beta, dx, in_dim, st));
   }
   return 0;
 }

@@ -19,6 +19,14 @@ def used_prefixes(model):
     """Name prefixes of the parameters that receive a gradient for THIS model configuration -- the set the reference's
     Adam actually updates (parameters whose grad stays None are skipped by torch.optim.Adam, weight decay included;
     SURVEY 8b "Used on GDF path").  Depends on graph_type / att_type / use_crn_speaker / reason_flag / layer count."""
+    if not getattr(model, "multi_modal", True):
+        # single-stream relation model: rnn_parties is constructed but unused (use_crn_speaker is off); with
+        # nodal_attention=False the attention's transform gets no gradient either
+        pre = ["linear_.", "lstm.", "att_model.scalar.", "graph_net.conv1.", "graph_net.conv2.", "graph_net.linear.",
+               "graph_net.smax_fc."]
+        if getattr(model, "nodal_attention", True):
+            pre.append("graph_net.matchatt.")
+        return tuple(pre)
     pre = ["linear_a.", "linear_v.", "linear_l.", "lstm_l.", "smax_fc."]
     if getattr(model, "use_crn_speaker", False):
         pre.append("rnn_parties.")

@@ -2,7 +2,8 @@
 import _bootstrap  # noqa: F401
 from mmdfn_b200.modules import (Attention, DialogueGNNModel, MaskedEdgeAttention, MatchingAttention,  # noqa: F401
                                 MMGatedAttention, SimpleAttention, simple_batch_graphify)
-from mmdfn_b200.relation import GraphNetwork, batch_graphify, edge_perms  # noqa: F401
+from mmdfn_b200.relation import (GraphNetwork, attentive_node_features, batch_graphify, classify_node_features,  # noqa: F401
+                                 edge_perms)
 
 
 def _outside_hot_path(name):

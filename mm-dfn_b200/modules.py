@@ -231,6 +231,12 @@ class MatchingAttention(nn.Module):
             self.transform = nn.Linear(cand_dim + mem_dim, alpha_dim, bias=False)
             self.vector_prod = nn.Linear(alpha_dim, 1, bias=False)
 
+    def forward(self, M, x, mask=None):
+        """The reference calls this once per candidate position t (code/model.py:637-640).  On the B200 path the whole
+        loop is one batched call on the ragged rows: `relation.attentive_node_features(..., matchatt_layer=self, ...)`."""
+        raise NotImplementedError("MatchingAttention: use mmdfn_b200.relation.attentive_node_features (all candidates of all "
+                                  "dialogues in one call, att_type='general2')")
+
 
 class Attention(nn.Module):
     def __init__(self, embed_dim, hidden_dim=None, out_dim=None, n_head=1, score_function='dot_product', dropout=0):
@@ -387,7 +393,17 @@ class DialogueGNNModel(nn.Module):
                  av_using_lstm=False, Deep_GCN_nlayers=64, dataset='IEMOCAP', use_speaker=True, use_modal=False,
                  reason_flag=False, multi_modal=True, use_crn_speaker=False, speaker_weights='1-1-1', modal_weight=1.0):
         super().__init__()
-        if base_model != 'LSTM' or not multi_modal or sorted(modals) != ['a', 'l', 'v'] \
+        # code/model.py:822-826: fusion types outside this list switch the model to the single-stream configuration
+        if att_type not in ('gated', 'concat_subsequently', 'mfn', 'mfn_only', 'tfn_only', 'lmf_only', 'concat_only'):
+            multi_modal = False
+        text_only = not multi_modal
+        if text_only:
+            # the DialogueGCN configuration (one feature stream U, `linear_` -> BiGRU `lstm` -> windowed relation graph ->
+            # nodal-attention head): code/model.py:828-849, 1035-1036, 1176-1180, 1211-1212
+            if base_model != 'LSTM' or graph_type != 'relation' or use_crn_speaker or use_GCN or D_e != 100 or avec:
+                raise NotImplementedError("single-stream (multi_modal=False) models: base_model='LSTM', graph_type='relation', "
+                                          "use_crn_speaker=False, use_GCN=False, D_e=100, avec=False")
+        elif base_model != 'LSTM' or sorted(modals) != ['a', 'l', 'v'] \
                 or graph_type not in ('GDF', 'relation') or av_using_lstm \
                 or not (att_type in ('concat_subsequently', 'mfn') or (att_type == 'gated' and graph_type == 'relation')) \
                 or D_e != 100 or graph_hidden_size != 100 or not use_residue or (graph_type == 'relation' and use_GCN):
@@ -411,6 +427,23 @@ class DialogueGNNModel(nn.Module):
         self.dataset = dataset
         self.window_past, self.window_future = window_past, window_future
         self.nodal_attention = nodal_attention
+        if text_only:
+            ms = ''.join(self.modals)
+            hidden_ = 250 if len(self.modals) == 3 else 150 if ms in ('al', 'vl') else 100          # code/model.py:829-838
+            self.linear_ = nn.Linear(D_m, hidden_)
+            self.lstm = nn.GRU(input_size=hidden_, hidden_size=D_e, num_layers=2, bidirectional=True, dropout=dropout)
+            self.rnn_parties = nn.GRU(input_size=hidden_, hidden_size=D_e, num_layers=2, bidirectional=True, dropout=dropout)
+            self.att_model = MaskedEdgeAttention(2 * D_e, max_seq_len, self.no_cuda)
+            from .relation import GraphNetwork
+            self.graph_net = GraphNetwork(2 * D_e, n_classes, 2 * n_speakers ** 2, max_seq_len, graph_hidden_size, dropout,
+                                          self.no_cuda, self.use_GCN)
+            print("construct relation graph")
+            self.edge_type_mapping = {}
+            for j in range(n_speakers):
+                for k in range(n_speakers):
+                    self.edge_type_mapping[str(j) + str(k) + '0'] = len(self.edge_type_mapping)
+                    self.edge_type_mapping[str(j) + str(k) + '1'] = len(self.edge_type_mapping)
+            return
 
         self.linear_a = nn.Linear(D_m_a, 200)
         self.linear_v = nn.Linear(D_m_v, 200)
@@ -462,6 +495,8 @@ class DialogueGNNModel(nn.Module):
             raise NotImplementedError("use_speaker / use_modal are off on the MM-DFN path")
         if not U.is_cuda:
             raise ops.MMDFNError("DialogueGNNModel.forward needs CUDA tensors: the B200 path has no CPU fallback")
+        if not self.multi_modal:
+            return self._forward_text_only(U, qmask, umask, seq_lengths, masks)
         T, B = U.shape[0], U.shape[1]
         S = qmask.shape[2]
         dev = U.device
@@ -531,6 +566,26 @@ class DialogueGNNModel(nn.Module):
         with ops.sink_key("head"):
             log_prob = ops.HeadFn.apply(F_, geom.N, m_h, scale, self.smax_fc.weight, self.smax_fc.bias)
         return log_prob, None, None, None, None
+
+    def _forward_text_only(self, U, qmask, umask, seq_lengths, masks=None):
+        """Single-stream `relation` model (code/model.py:1035-1036, 1176-1180, 1211-1212): linear_ -> 2-layer BiGRU ->
+        batch_graphify (windowed speaker/temporal edges, MaskedEdgeAttention norms) -> RGCN -> GraphConv -> nodal-attention
+        head.  `masks` (tests only): {'gru': (T,B,200) keep mask of the inter-layer dropout, 'head': (N, hidden) keep mask}."""
+        from .relation import batch_graphify
+        T, B = U.shape[0], U.shape[1]
+        mk = masks or {}
+        p = float(self.dropout)
+        x = ops.LinearFn.apply(U, self.linear_.weight, self.linear_.bias)
+        m_g = mk.get("gru")
+        if m_g is None and self.training and p > 0 and masks is None:
+            m_g = ops.make_mask((T, B, 200), p, U.device)
+        scale = 1.0 / (1.0 - p) if m_g is not None else 1.0
+        emotions = ops.BiGRU2Fn.apply(x.reshape(T * B, x.shape[-1]), None, T, B, m_g, scale, *self._gru_weights(self.lstm))
+        features, edge_index, edge_norm, edge_type, edge_index_lengths = batch_graphify(
+            emotions, qmask, seq_lengths, self.window_past, self.window_future, self.edge_type_mapping, self.att_model, self.no_cuda)
+        log_prob = self.graph_net(features, edge_index, edge_norm, edge_type, seq_lengths, umask, self.nodal_attention, self.avec,
+                                  mask=mk.get("head"))
+        return log_prob, edge_index, edge_norm, edge_type, edge_index_lengths
 
     def _mfn_head(self, F_, geom, T, perm, mk):
         """att_type='mfn' (code/model.py:1263-1291, 1303-1330): the node features, padded per dialogue to (T, B, 900), go

@@ -379,7 +379,8 @@ def plan_gru_tiles(T, n_a, n_b, sms=148):
 
 
 class BiGRU2Fn(torch.autograd.Function):
-    """x (rows,200) [+ rowmap (T,nseq) gather] -> y (T,nseq,200).  16 weights in GRU_KEYS order."""
+    """x (rows, in_dim) [+ rowmap (T,nseq) gather] -> y (T,nseq,200).  16 weights in GRU_KEYS order; in_dim = 200 on the
+    MM-DFN path, the width of `linear_` in the text-only configuration."""
 
     @staticmethod
     def forward(ctx, x, rowmap, T, nseq, mask, mask_scale, *w):
@@ -393,7 +394,7 @@ class BiGRU2Fn(torch.autograd.Function):
         ctx.sink_key = _SINK_KEY[0]
         call("mmdfn_gru_set_tile", ctx.tile)
         try:
-            call("mmdfn_bigru2_fwd", T, nseq, rows, ptr(x), ptr(rowmap, torch.int32), tab, ptr(mask, U8),
+            call("mmdfn_bigru2_fwd_in", x.shape[1], T, nseq, rows, ptr(x), ptr(rowmap, torch.int32), tab, ptr(mask, U8),
                  float(mask_scale), ptr(y), ptr(ws), stream())
         finally:
             call("mmdfn_gru_set_tile", 0)
@@ -420,7 +421,7 @@ class BiGRU2Fn(torch.autograd.Function):
         tab, dtab = ptr_table(w), ptr_table(dw)
         call("mmdfn_gru_set_tile", ctx.tile)
         try:
-            call("mmdfn_bigru2_bwd", T, nseq, rows, ptr(x), ptr(ctx.rowmap, torch.int32), tab, ptr(ctx.mask, U8),
+            call("mmdfn_bigru2_bwd_in", x.shape[1], T, nseq, rows, ptr(x), ptr(ctx.rowmap, torch.int32), tab, ptr(ctx.mask, U8),
                  ctx.mask_scale, ptr(y), ptr(dy), ptr(ws), ptr(dx), 0, dtab, 1, ptr(wsb), stream())
         finally:
             call("mmdfn_gru_set_tile", 0)
@@ -608,6 +609,51 @@ class ReluMaskFn(torch.autograd.Function):
         dx = _empty(y.shape, y.device)
         call("mmdfn_relu_mask_bwd", y.numel(), ptr(dy), ptr(y), ctx.ind, ptr(dx), stream())
         return dx, None, None
+
+
+# ---------------------------------------------------------------------------------------------
+# k13 (f3): nodal attention of the relation path's classifier head
+# ---------------------------------------------------------------------------------------------
+class NodalGeom:
+    """per-dialogue L x L block offsets and the dialogue index of every node row (device), built once per batch geometry"""
+
+    def __init__(self, lengths, device):
+        self.lengths = [int(x) for x in lengths]
+        self.B, self.N = len(self.lengths), int(sum(self.lengths))
+        self.Lmax = int(max(self.lengths)) if self.lengths else 0
+        sq = [0] + list(itertools.accumulate(L * L for L in self.lengths))
+        self.nsq = sq[-1]
+        self.dia_off = torch.tensor([0] + list(itertools.accumulate(self.lengths)), dtype=torch.int32).to(device)
+        self.sq_off = torch.tensor(sq, dtype=torch.int64).to(device)
+        self.row_dia = torch.tensor([b for b, L in enumerate(self.lengths) for _ in range(L)], dtype=torch.int32).to(device)
+
+
+class NodalAttnFn(torch.autograd.Function):
+    """O_b = softmax_rows(tanh(Q_b E_b^T)) E_b per dialogue (code/model.py:614-645 with MatchingAttention 'general2', :66-76);
+    Q = transform(E) comes from LinearFn, so autograd adds the projection's path (dE += dQ W, dW, db) itself."""
+
+    @staticmethod
+    def forward(ctx, E, Q, g):
+        E, Q = _f32c(E), _f32c(Q)
+        N, D = E.shape
+        P, S = _empty((max(g.nsq, 1),), E.device), _empty((max(g.nsq, 1),), E.device)
+        O = _empty((N, D), E.device)
+        call("mmdfn_nodal_attn_fwd", g.B, N, D, g.Lmax, ptr(g.dia_off, torch.int32), ptr(g.sq_off, torch.int64),
+             ptr(g.row_dia, torch.int32), ptr(E), ptr(Q), ptr(P), ptr(S), ptr(O), stream())
+        ctx.save_for_backward(E, Q, P, S)
+        ctx.g = g
+        return O
+
+    @staticmethod
+    def backward(ctx, dO):
+        E, Q, P, S = ctx.saved_tensors
+        g, (N, D) = ctx.g, E.shape
+        dO = _f32c(dO)
+        dA = _empty((max(g.nsq, 1),), E.device)
+        dQ, dE = _empty((N, D), E.device), _empty((N, D), E.device)
+        call("mmdfn_nodal_attn_bwd", g.B, N, D, g.Lmax, ptr(g.dia_off, torch.int32), ptr(g.sq_off, torch.int64),
+             ptr(g.row_dia, torch.int32), ptr(E), ptr(Q), ptr(P), ptr(S), ptr(dO), ptr(dA), ptr(dQ), ptr(dE), stream())
+        return dE, dQ, None
 
 
 # ---------------------------------------------------------------------------------------------

@@ -334,19 +334,74 @@ class GraphConv(torch.nn.Module):
         return GraphConvFn.apply(x, self.weight, self.lin.weight, self.lin.bias, _edges_of(edge_index))
 
 
+def attentive_node_features(emotions, seq_lengths, umask, matchatt_layer, no_cuda=False):
+    """code/model.py:614-645 (Eq. 4-6 of DialogueGCN): every node attends over the nodes of its own dialogue through
+    MatchingAttention('general2').  emotions: ragged (N, D) node features.  Returns the attentive features of the VALID
+    rows, ragged (N, D) -- the reference returns the padded (T, B, D) tensor, whose padded rows its only caller
+    (`classify_node_features`, :663) drops again; `umask` is implied by `seq_lengths` and only checked for shape."""
+    if getattr(matchatt_layer, "att_type", None) != 'general2':
+        raise NotImplementedError("attentive_node_features: only MatchingAttention(att_type='general2') (code/model.py:685)")
+    if not emotions.is_cuda:
+        raise MMDFNError("attentive_node_features needs CUDA tensors: the B200 path has no CPU fallback")
+    lengths = [int(x) for x in seq_lengths]
+    if umask is not None and (umask.shape[0] != len(lengths) or umask.shape[1] < max(lengths)):
+        raise ValueError("umask does not match seq_lengths")
+    g = _nodal_geom(lengths, emotions.device)
+    q = ops.LinearFn.apply(emotions, matchatt_layer.transform.weight, matchatt_layer.transform.bias)
+    return ops.NodalAttnFn.apply(emotions, q, g)
+
+
+def _nodal_geom(lengths, device, cache={}):
+    key = (tuple(lengths), str(device))
+    g = cache.get(key)
+    if g is None:
+        if len(cache) > 64:
+            cache.clear()
+        g = cache[key] = ops.NodalGeom(lengths, device)
+    return g
+
+
+def classify_node_features(emotions, seq_lengths, umask, matchatt_layer, linear_layer, dropout_layer, smax_fc_layer, nodal_attn,
+                           avec, no_cuda=False, mask=None):
+    """code/model.py:647-672: (nodal attention ->) relu(linear) -> dropout -> smax_fc -> log_softmax over the ragged (N, .)
+    rows.  `mask` (tests only): (N, hidden) uint8 keep mask injected instead of a drawn one."""
+    if nodal_attn:
+        emotions = attentive_node_features(emotions, seq_lengths, umask, matchatt_layer, no_cuda)
+    hidden = ops.LinearFn.apply(emotions, linear_layer.weight, linear_layer.bias)
+    p = float(dropout_layer.p)
+    if mask is None and dropout_layer.training and p > 0:
+        mask = ops.make_mask(tuple(hidden.shape), p, hidden.device)
+    hidden = ops.ReluMaskFn.apply(hidden, mask, 1.0 / (1.0 - p) if mask is not None else 1.0)
+    hidden = ops.LinearFn.apply(hidden, smax_fc_layer.weight, smax_fc_layer.bias)
+    if avec:
+        return hidden
+    return ops.LogSoftmaxFn.apply(hidden)
+
+
 class GraphNetwork(torch.nn.Module):
-    """code/model.py:675-715 with return_feature=True (the multi-modal relation configuration): cat([x, conv2(conv1(x))])."""
+    """code/model.py:675-715: cat([x, conv2(conv1(x))]); with return_feature=False (the text-only DialogueGCN configuration)
+    followed by the nodal-attention classifier head (`classify_node_features`)."""
 
     def __init__(self, num_features, num_classes, num_relations, max_seq_len, hidden_size=64, dropout=0.5, no_cuda=False,
                  use_GCN=False, return_feature=False):
         super().__init__()
-        if use_GCN or not return_feature:
-            raise NotImplementedError("only use_GCN=False, return_feature=True (nodal-attention head is out of scope)")
+        if use_GCN:
+            raise NotImplementedError("only use_GCN=False (the GCNLayer1 side branch is an out-of-scope baseline)")
         self.return_feature, self.no_cuda, self.use_GCN = return_feature, no_cuda, use_GCN
         self.conv1 = RGCNConv(num_features, hidden_size, num_relations, num_bases=30)
         self.conv2 = GraphConv(hidden_size, hidden_size)
+        if not self.return_feature:
+            from .modules import MatchingAttention
+            self.matchatt = MatchingAttention(num_features + hidden_size, num_features + hidden_size, att_type='general2')
+            self.linear = torch.nn.Linear(num_features + hidden_size, hidden_size)
+            self.dropout = torch.nn.Dropout(dropout)
+            self.smax_fc = torch.nn.Linear(hidden_size, num_classes)
 
-    def forward(self, x, edge_index, edge_norm, edge_type, seq_lengths, umask, nodal_attn, avec):
+    def forward(self, x, edge_index, edge_norm, edge_type, seq_lengths, umask, nodal_attn, avec, mask=None):
         out = self.conv1(x, edge_index, edge_type, edge_norm)
         out = self.conv2(out, edge_index)
-        return torch.cat([x, out], dim=-1)
+        emotions = torch.cat([x, out], dim=-1)
+        if self.return_feature:
+            return emotions
+        return classify_node_features(emotions, seq_lengths, umask, self.matchatt, self.linear, self.dropout, self.smax_fc,
+                                      nodal_attn, avec, self.no_cuda, mask=mask)

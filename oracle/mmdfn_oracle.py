@@ -573,6 +573,36 @@ def mfn_head(feat: Tensor, lengths: Sequence[int], P: Dict[str, Tensor], masks: 
 
 
 # --------------------------------------------------------------------------------------
+# f3 (☆): nodal-attention head of the `relation` graph type (text-only DialogueGCN configuration)
+# --------------------------------------------------------------------------------------
+def nodal_attention(E: Tensor, lengths: Sequence[int], w_t: Tensor, b_t: Tensor) -> Tensor:
+    """attentive_node_features (code/model.py:614-645) with MatchingAttention('general2') (:66-76, :83-84), restated on
+    the ragged rows.  For dialogue b with rows E_b (L, D): x_ = transform(x_t) = W x_t + b; alpha_ = tanh(x_ . M_s) on the
+    valid positions (0 on the padded ones), softmax over ALL positions, re-masked and re-normalised -- the padded
+    positions' exp(0) cancels, leaving a softmax of tanh(scores) over the valid positions; pool = sum_s alpha_s M_s.
+    (The reference also evaluates padded candidates t >= L; classify_node_features drops them, :663.)"""
+    out, off = [], 0
+    for L in lengths:
+        Eb = E[off:off + L]
+        Q = Eb @ w_t.t() + b_t
+        P = torch.softmax(torch.tanh(Q @ Eb.t()), dim=1)
+        out.append(P @ Eb)
+        off += L
+    return torch.cat(out, 0)
+
+
+def nodal_head(E: Tensor, lengths: Sequence[int], P: Dict[str, Tensor], mask: Optional[Tensor] = None, scale: float = 1.0,
+               prefix: str = "") -> Tensor:
+    """classify_node_features(nodal_attn=True, avec=False) (code/model.py:647-664): attentive features ->
+    relu(linear) -> dropout (`mask`: (N, hidden) keep mask, None = identity) -> smax_fc -> log_softmax."""
+    att = nodal_attention(E, lengths, P[prefix + "matchatt.transform.weight"], P[prefix + "matchatt.transform.bias"])
+    hid = torch.relu(att @ P[prefix + "linear.weight"].t() + P[prefix + "linear.bias"])
+    if mask is not None:
+        hid = hid * mask.to(hid.dtype) * scale
+    return torch.log_softmax(hid @ P[prefix + "smax_fc.weight"].t() + P[prefix + "smax_fc.bias"], dim=1)
+
+
+# --------------------------------------------------------------------------------------
 # deterministic, torch-version-independent weights and synthetic inputs (shared by the
 # golden generator, the tests and bench.py so that nothing has to travel to the GPU box)
 # --------------------------------------------------------------------------------------
