@@ -287,6 +287,18 @@ int mmdfn_window_sum(int N, int G, int reach_back, int reach_fwd, const int* dia
 /* out[b][c][r] = in[b][r][c] */
 int mmdfn_transpose_batched(int batch, int rows, int cols, const float* in, float* out, void* stream);
 
+/* ---- ☆ f4: low-rank multimodal fusion (LMF, code/model_fusion.py:214-310; att_type = 'lmf_only') -------------------
+ * out = sum_r w_r prod_m ([1, h_m] . factor_m[r]) + bias with h: three (N, H) activations {audio, video, text} (the
+ * sub-network Linears run on mmdfn_gemm), factor: three (R, H + 1, O) tensors (row 0 = the weight of the appended 1),
+ * w (R) = fusion_weights, bias (O); R <= 8.  fz / dfz: 3 R N O floats (mmdfn_lmf_ws_floats); fz is saved for backward.
+ * _bwd overwrites dh[m], dfactor[m], dbias and ACCUMULATES into dw (zero it first). */
+long long mmdfn_lmf_ws_floats(int N, int R, int O);
+int mmdfn_lmf_fuse_fwd(int N, int H, int O, int R, const float* const* h, const float* const* factor, const float* w,
+                       const float* bias, float* fz, float* out, void* stream);
+int mmdfn_lmf_fuse_bwd(int N, int H, int O, int R, const float* const* h, const float* const* factor, const float* w,
+                       const float* fz, const float* dout, float* dfz, float* const* dh, float* const* dfactor, float* dw,
+                       float* dbias, void* stream);
+
 /* ---- k13 (☆ SURVEY 8f rank 3): nodal attention of the relation path's classifier head ---------------------------
  * Replaces attentive_node_features + MatchingAttention('general2') (code/model.py:614-645, 66-76) on the ragged node
  * rows: per dialogue b (rows dia_off[b]..dia_off[b+1]-1 of E, Q, O: (N, D), D <= 512)

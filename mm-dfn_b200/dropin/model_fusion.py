@@ -1,6 +1,6 @@
-"""Drop-in for the reference's `code/model_fusion.py` (imported by code/model.py:992 for att_type 'mfn')."""
+"""Drop-in for the reference's `code/model_fusion.py` (imported by code/model.py:992-1001 for att_type 'mfn' / 'lmf_only')."""
 import _bootstrap  # noqa: F401
-from mmdfn_b200.modules import MFN  # noqa: F401
+from mmdfn_b200.modules import LMF, MFN  # noqa: F401
 
 
 def _outside_hot_path(name):
@@ -12,4 +12,3 @@ def _outside_hot_path(name):
 
 
 TFN = _outside_hot_path("TFN")
-LMF = _outside_hot_path("LMF")

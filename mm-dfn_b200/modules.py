@@ -327,6 +327,49 @@ def simple_batch_graphify(features, lengths, no_cuda):
 # code/model.py:784-1407
 # ------------------------------------------------------------------------------------------------
 # ------------------------------------------------------------------------------------------------
+# code/model_fusion.py:214-310
+# ------------------------------------------------------------------------------------------------
+class LMF(nn.Module):
+    """Low-rank multimodal fusion (Liu et al., ACL 2018) as the reference builds it (code/model_fusion.py:220-273): the same
+    sub-modules and parameters in the same order with the same initialisers (identical state_dict keys and seed-for-seed
+    initial weights); forward(audio_x, video_x, text_x) with three (N, 300) inputs -> (N, output_dim) runs on the CUDA
+    path (the sub-network Linears on mmdfn_gemm, the rank products and their combination in mmdfn_lmf_fuse_fwd / _bwd).
+    `post_fusion_dropout` is constructed and, as in the reference's forward, never applied."""
+
+    def __init__(self, input_dims=(300, 300, 300), hidden_dims=(300, 300, 300), dropouts=0.4, output_dim=300, rank=4, use_softmax=False):
+        super().__init__()
+        if use_softmax or len(set(hidden_dims)) != 1 or rank > 8:
+            raise NotImplementedError("LMF: equal hidden sizes, rank <= 8, use_softmax=False (the reference's defaults)")
+        self.audio_in, self.video_in, self.text_in = input_dims
+        self.audio_hidden, self.video_hidden, self.text_hidden = hidden_dims
+        self.audio_subnet = nn.Linear(self.audio_in, self.audio_hidden)
+        self.video_subnet = nn.Linear(self.video_in, self.video_hidden)
+        self.text_subnet = nn.Linear(self.text_in, self.text_hidden)
+        self.output_dim, self.rank, self.use_softmax = output_dim, rank, use_softmax
+        self.audio_prob = self.video_prob = self.text_prob = self.post_fusion_prob = dropouts
+        self.post_fusion_dropout = nn.Dropout(p=dropouts)
+        self.audio_factor = Parameter(torch.Tensor(self.rank, self.audio_hidden + 1, self.output_dim))
+        self.video_factor = Parameter(torch.Tensor(self.rank, self.video_hidden + 1, self.output_dim))
+        self.text_factor = Parameter(torch.Tensor(self.rank, self.text_hidden + 1, self.output_dim))
+        self.fusion_weights = Parameter(torch.Tensor(1, self.rank))
+        self.fusion_bias = Parameter(torch.Tensor(1, self.output_dim))
+        nn.init.xavier_normal_(self.audio_factor)
+        nn.init.xavier_normal_(self.video_factor)
+        nn.init.xavier_normal_(self.text_factor)
+        nn.init.xavier_normal_(self.fusion_weights)
+        self.fusion_bias.data.fill_(0)
+
+    def forward(self, audio_x, video_x, text_x):
+        if not audio_x.is_cuda:
+            raise ops.MMDFNError("LMF.forward needs CUDA tensors: the B200 path has no CPU fallback")
+        ha = ops.LinearFn.apply(audio_x, self.audio_subnet.weight, self.audio_subnet.bias)
+        hv = ops.LinearFn.apply(video_x, self.video_subnet.weight, self.video_subnet.bias)
+        ht = ops.LinearFn.apply(text_x, self.text_subnet.weight, self.text_subnet.bias)
+        return ops.LMFFuseFn.apply(ha, hv, ht, self.audio_factor, self.video_factor, self.text_factor, self.fusion_weights,
+                                   self.fusion_bias)
+
+
+# ------------------------------------------------------------------------------------------------
 # code/model_fusion.py:10-120
 # ------------------------------------------------------------------------------------------------
 class MFN(nn.Module):

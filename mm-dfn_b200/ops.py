@@ -612,6 +612,45 @@ class ReluMaskFn(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------------
+# f4: low-rank multimodal fusion (LMF)
+# ---------------------------------------------------------------------------------------------
+class LMFFuseFn(torch.autograd.Function):
+    """out = sum_r w_r prod_m ([1, h_m] . factor_m[r]) + bias (code/model_fusion.py:292-305); h_m (N, H) from the three
+    sub-network Linears, factor_m (R, H + 1, O), w (1, R), bias (1, O)."""
+
+    @staticmethod
+    def forward(ctx, ha, hv, ht, fa, fv, ft, w, bias):
+        hs = [_f32c(x) for x in (ha, hv, ht)]
+        fs = [_f32c(x) for x in (fa, fv, ft)]
+        w, bias = _f32c(w), _f32c(bias)
+        N, H = hs[0].shape
+        R, _, O = fs[0].shape
+        fz = _empty((query("mmdfn_lmf_ws_floats", N, R, O),), ha.device)
+        out = _empty((N, O), ha.device)
+        ht_, ft_ = ptr_table(hs), ptr_table(fs)
+        call("mmdfn_lmf_fuse_fwd", N, H, O, R, ht_, ft_, ptr(w), ptr(bias), ptr(fz), ptr(out), stream())
+        ctx.save_for_backward(*hs, *fs, w, fz)
+        ctx.dims = (N, H, O, R)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        hs, fs = list(ctx.saved_tensors[:3]), list(ctx.saved_tensors[3:6])
+        w, fz = ctx.saved_tensors[6], ctx.saved_tensors[7]
+        N, H, O, R = ctx.dims
+        dev = dout.device
+        dout = _f32c(dout)
+        dfz = _empty((max(3 * R * N * O, 1),), dev)
+        dh = [_empty((N, H), dev) for _ in range(3)]
+        df = [_empty((R, H + 1, O), dev) for _ in range(3)]
+        dw = torch.zeros((1, R), device=dev, dtype=torch.float32)
+        dbias = _empty((1, O), dev)
+        call("mmdfn_lmf_fuse_bwd", N, H, O, R, ptr_table(hs), ptr_table(fs), ptr(w), ptr(fz), ptr(dout), ptr(dfz), ptr_table(dh),
+             ptr_table(df), ptr(dw), ptr(dbias), stream())
+        return (*dh, *df, dw, dbias)
+
+
+# ---------------------------------------------------------------------------------------------
 # k13 (f3): nodal attention of the relation path's classifier head
 # ---------------------------------------------------------------------------------------------
 class NodalGeom:

@@ -573,6 +573,22 @@ def mfn_head(feat: Tensor, lengths: Sequence[int], P: Dict[str, Tensor], masks: 
 
 
 # --------------------------------------------------------------------------------------
+# f4 (☆): low-rank multimodal fusion, code/model_fusion.py:214-310 (att_type='lmf_only')
+# --------------------------------------------------------------------------------------
+def lmf_forward(xa: Tensor, xv: Tensor, xt: Tensor, P: Dict[str, Tensor], prefix: str = "") -> Tensor:
+    """LMF.forward (:275-310): per modality h = Linear(x); fusion_m = [1, h] . factor_m (rank, 301, 300) -> (rank, N, 300);
+    out = fusion_weights (1, rank) . (fusion_a * fusion_v * fusion_t) + fusion_bias."""
+    fz = None
+    for x, n in ((xa, "audio"), (xv, "video"), (xt, "text")):
+        h = linear(x, P[f"{prefix}{n}_subnet.weight"], P[f"{prefix}{n}_subnet.bias"])
+        h1 = torch.cat([torch.ones(h.shape[0], 1, dtype=h.dtype), h], dim=1)
+        f = torch.matmul(h1, P[f"{prefix}{n}_factor"])                       # (rank, N, 300)
+        fz = f if fz is None else fz * f
+    out = torch.matmul(P[prefix + "fusion_weights"], fz.permute(1, 0, 2)).squeeze(1) + P[prefix + "fusion_bias"]
+    return out.view(-1, P[prefix + "fusion_bias"].shape[1])
+
+
+# --------------------------------------------------------------------------------------
 # f3 (☆): nodal-attention head of the `relation` graph type (text-only DialogueGCN configuration)
 # --------------------------------------------------------------------------------------
 def nodal_attention(E: Tensor, lengths: Sequence[int], w_t: Tensor, b_t: Tensor) -> Tensor:

@@ -66,10 +66,10 @@ def test_graph_replays_match_eager_steps():
     # first steps move a parameter by ~lr * sign(g): an element whose gradient is at the noise level may flip, so a max-abs
     # bound over 1.2 M parameters is a coin toss (seen failing once at 3.4e-4 on an unchanged build).  A wrong step index
     # or bias correction would shift EVERY update by tens of percent: bound the relative distance of the whole update and
-    # the fraction of elements that moved differently.
+    # the fraction of elements that moved differently (observed run to run: distance <= 2e-3, fraction <= 4e-4).
     d_e, d_g = p_eager - p_init, tr_g.flat_p - p_init
-    assert float((d_g - d_e).norm() / d_e.norm()) < 2e-3
-    assert float(((d_g - d_e).abs() > 5e-5).float().mean()) < 1e-4
+    assert float((d_g - d_e).norm() / d_e.norm()) < 1e-2
+    assert float(((d_g - d_e).abs() > 5e-5).float().mean()) < 2e-3
 
 
 def test_graph_replays_draw_fresh_dropout_masks():
