@@ -152,6 +152,17 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
     ke = min(p.K, kb + chunk);
   }
   const int nchunks = ke > kb ? (ke - kb + G3_KC - 1) / G3_KC : 0;
+  // K order: every CTA walks its 32-wide K panels in a ROTATED order (start panel = a function of the tile index).  All
+  // CTAs of a column tile read the same B rows; in lockstep they requested the same few cache lines at the same time and
+  // the loads queued at those L2 lines (in-kernel stamps: ~2.7 k cycles to get five 16-byte loads per thread issued).
+  // Chunk slot c -> chunk kchunk(c); an odd chunk count gets one phantom slot (its MMAs are skipped).
+  const int npan = (nchunks + 1) >> 1, nslots = 2 * npan;
+  const int prot = npan > 0 ? (int)((blockIdx.x + 7u * blockIdx.y + 3u * blockIdx.z) % (unsigned)npan) : 0;
+  auto kchunk = [&](int c) {
+    int ap = (c >> 1) + prot;
+    if (ap >= npan) ap -= npan;
+    return 2 * ap + (c & 1);
+  };
 
   // ---- per-thread operand pieces ----
   const int q = warp & 3, g = warp >> 2;                     // converter warp: TMEM lane quarter, group
@@ -213,12 +224,13 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
   const i64 astep = (i64)G3_KC * p.lda;
   float4 ra[A_KMAJ ? 1 : 4], rb[NPB];
   auto prefetch = [&](int c) {
-    if (c >= nchunks) return;
-    const int k0 = kb + c * G3_KC;
+    if (c >= nslots) return;
+    const int cc = kchunk(c);
+    const int k0 = kb + cc * G3_KC;
     if (k0 + G3_KC <= ke) {
       // every k of the chunk is inside the contraction range: no per-element checks
       if (!A_KMAJ) {
-        const float* a = aptr + (i64)c * astep;
+        const float* a = aptr + (i64)cc * astep;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -237,7 +249,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bok[i] && p.dbg != 7) {
           if (B_KMAJ) {
-            v = __ldg(reinterpret_cast<const float4*>(bptr[i] + c * G3_KC));
+            v = __ldg(reinterpret_cast<const float4*>(bptr[i] + cc * G3_KC));
           } else {
             const float* b = brow(k0 + 4 * b_kq[i]) + b_row[i];
             v.x = __ldg(b);
@@ -273,17 +285,19 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
     const uint32_t d0_hi = (uint32_t)(d0 >> 32), d0_lo = (uint32_t)d0;
     int s = 0;
     uint32_t par = 0;
-    for (int c = 0; c < nchunks; c++) {
+    uint32_t started = 0;
+    for (int c = 0; c < nslots; c++) {
       umma::mbar_wait(&bar_full[s], par);
       umma::tc_fence_after_sync();
-      const int kleft = ke - (kb + c * G3_KC);
-      const int ksteps = kleft >= G3_KC ? 2 : (kleft + 7) >> 3;
+      const int kleft = ke - (kb + kchunk(c) * G3_KC);
+      const int ksteps = kleft >= G3_KC ? 2 : kleft > 0 ? (kleft + 7) >> 3 : 0;       // 0: the phantom slot of an odd chunk count
       const uint32_t acol = tm_a + 32u * (uint32_t)s;
       for (int j = 0; j < ksteps; j++) {
         const uint32_t dlo = d0_lo + (uint32_t)((s * stage_bytes + j * 2 * G3_LBO) >> 4);
         const uint64_t b_hi = ((uint64_t)d0_hi << 32) | dlo;
         const uint64_t b_lo = ((uint64_t)d0_hi << 32) | (dlo + (uint32_t)(bpart >> 4));
-        const uint32_t acc = (c > 0 || j > 0) ? 1u : 0u;
+        const uint32_t acc = started;
+        started = 1u;
         if (p.dbg == 1) continue;
         umma::mma_tf32_ta_elect(tmem, tmem + acol + 8u * j, b_hi, idesc, acc);
         umma::mma_tf32_ta_elect(tmem + tm_corr, tmem + acol + 16u + 8u * j, b_hi, idesc, acc);
@@ -302,11 +316,10 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
   if (warp == G3_CONVW + 1) {
     // ===== raw-A producer (K-contiguous A only): one bulk copy per tile row per panel =====
     if (A_KMAJ) {
-      const int npan = (nchunks + 1) >> 1;
       for (int pp = 0; pp < npan; pp++) {
         const int slot = pp % G3_NP, use = pp / G3_NP;
         if (use > 0) umma::mbar_wait(&raw_free[slot], (uint32_t)((use - 1) & 1));
-        const int kp = kb + 32 * pp;
+        const int kp = kb + G3_KC * kchunk(2 * pp);
         const uint32_t bar = umma::smem_u32(&raw_full[slot]);
         if (lane == 0) {
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)G3_PANEL) : "memory");
@@ -325,7 +338,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
   const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
   const bool stamp_on = p.stamps != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
 #define G3_STAMP(slot) do { if (stamp_on && c < 32) p.stamps[8 * (c >> 2) + (slot)] = clock64(); } while (0)
-  for (int c = g; c < nchunks; c += G3_GROUPS) {
+  for (int c = g; c < nslots; c += G3_GROUPS) {
     const int use = c / ns, s = c - use * ns;
     G3_STAMP(0);
     if (use > 0) {
@@ -380,12 +393,14 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
       *reinterpret_cast<float4*>(st + bpart + b_off[i]) = l;
     }
     G3_STAMP(4);
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    G3_STAMP(5);
-    umma::tc_fence_before_sync();
-    umma::warp_arrive_full(&bar_full[s]);
-    G3_STAMP(6);
+    // the next chunk's global loads go out BEFORE the hand-off: issued after the proxy fence they sat behind it for ~2.7 k
+    // cycles (in-kernel stamps), a third of a group's iteration
     prefetch(c + G3_GROUPS);
+    G3_STAMP(5);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    umma::tc_fence_before_sync();
+    G3_STAMP(6);
+    umma::warp_arrive_full(&bar_full[s]);
     G3_STAMP(7);
   }
 #undef G3_STAMP
