@@ -66,7 +66,10 @@ def test_two_gpu_gradients_match_single_gpu(tmp_path):
     g1 = tr.flat_g.cpu()
     assert abs(float(loss) - float(r0["loss"])) < 1e-5
     assert float((r0["g"] - g1).norm() / g1.norm()) < 1e-4                          # 1-GPU vs 2-GPU gradient equality
-    assert float((r0["p"] - tr.flat_p.cpu()).abs().max()) < 1e-5                    # same Adam step
+    # same Adam step: the first step moves every parameter by lr * g / (|g| + eps); for the few elements whose gradient is of
+    # the order of eps = 1e-8 a last-bit difference of the 2-GPU sum moves that ratio by ~1 % (seen: 1.07e-5 at lr = 1e-3),
+    # a wrong step would be off by ~lr
+    assert float((r0["p"] - tr.flat_p.cpu()).abs().max()) < 5e-5
 
 
 def test_training_steps_reduce_loss():
