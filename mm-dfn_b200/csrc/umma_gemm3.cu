@@ -38,7 +38,12 @@ namespace mmdfn {
 constexpr int G3_KC = 16;
 constexpr int G3_CONVW = 16, G3_CONV = 32 * G3_CONVW, G3_THREADS = G3_CONV + 64;     // + MMA warp + raw-A producer warp
 constexpr int G3_LBO = 128, G3_SBO = 528;
-constexpr int G3_BN_MAX = 192, G3_NS_MAX = 6;
+// stages = converter groups: chunk c and chunk c + 4 are converted by the same group, so a stage (shared-memory B chunk +
+// tensor-memory A chunk) is only ever rewritten by the warps that wrote it before, after the mbarrier that the MMAs'
+// tcgen05.commit completes -- program order plus that barrier, which also keeps compute-sanitizer's racecheck (it does
+// not follow the commit -> mbarrier edge across warps) free of false reports.  Deeper rings (6) measured no faster: a
+// group's iteration (~4 k cycles) is far longer than its chunk's MMAs (~0.5 k).
+constexpr int G3_BN_MAX = 192, G3_NS_MAX = 4;
 constexpr int G3_GROUPS = 4;                               // converter groups (4 warps = 128 threads each)
 // raw panels of a K-contiguous A: 2 chunks (32 floats = 128 B) of each of the 128 tile rows = one 16 KB box of a 2-D
 // tensor map (ONE cp.async.bulk.tensor per panel; rows / columns outside the matrix arrive as zeros).  SWIZZLE_128B:
@@ -406,6 +411,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) umma_gemm3_kernel(const __grid_
 #undef G3_STAMP
   umma::mbar_wait(&bar_done, 0);
   umma::tc_fence_after_sync();
+  asm volatile("bar.sync 1, %0;" ::"n"(G3_CONV) : "memory");      // the scratch below aliases stages written by other warps
 
   // ---- epilogue: 32 x 32 panels, TMEM -> registers -> padded scratch -> lanes along the row ----
   float* scr = reinterpret_cast<float*>(smem + warp * G3_SCRATCH);

@@ -30,9 +30,16 @@ def used_prefixes(model):
     pre = ["linear_a.", "linear_v.", "linear_l.", "lstm_l.", "smax_fc."]
     if getattr(model, "use_crn_speaker", False):
         pre.append("rnn_parties.")
-    if getattr(model, "att_type", "") == "mfn":
+    if getattr(model, "att_type", "") in ("mfn", "mfn_only"):
         # out_fc1 / out_fc2 of the memory fusion network are constructed but never used: no gradient, Adam skips them
         pre += ["mfn.lstm_", "mfn.att1_", "mfn.att2_", "mfn.gamma1_", "mfn.gamma2_"]
+    if getattr(model, "graph_type", "GDF") == "None":
+        pre += ["graph_net_a.", "graph_net_v.", "graph_net_l."]
+        if model.att_type == "gated":
+            pre.append("gatedatt.")
+        if model.att_type == "lmf_only":
+            pre.append("lmf.")
+        return tuple(pre)
     if getattr(model, "graph_type", "GDF") == "relation":
         pre += ["graph_net_a.", "graph_net_v.", "graph_net_l.", "att_model.scalar."]
         if getattr(model, "att_type", "") == "gated":
@@ -66,7 +73,7 @@ def gradient_groups(model):
     """[(sink key, [parameters in the order of the backward function's internal gradient buffer])] for the GDF model,
     early-final groups first: the head and graph-stack gradients are complete ~1 ms before the encoder gradients, so
     they form the first all-reduce bucket.  None for configurations whose functions do not write into a sink."""
-    if getattr(model, "graph_type", None) != "GDF" or getattr(model, "att_type", "") == "mfn":
+    if getattr(model, "graph_type", None) not in ("GDF", "GF") or getattr(model, "att_type", "") == "mfn":
         return None
     from . import ops
     net = model.graph_model.graph_net

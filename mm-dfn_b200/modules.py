@@ -446,13 +446,20 @@ class DialogueGNNModel(nn.Module):
             if base_model != 'LSTM' or graph_type != 'relation' or use_crn_speaker or use_GCN or D_e != 100 or avec:
                 raise NotImplementedError("single-stream (multi_modal=False) models: base_model='LSTM', graph_type='relation', "
                                           "use_crn_speaker=False, use_GCN=False, D_e=100, avec=False")
+        elif graph_type == 'None':
+            # graph-free multimodal baselines (code/model.py:952-961, 1338-1405): per-modality Linear(200 -> 100) on the encoder
+            # features, [that | features] per modality, one of the fusion blocks, dropout -> smax_fc -> log_softmax
+            if base_model != 'LSTM' or sorted(modals) != ['a', 'l', 'v'] or av_using_lstm or D_e != 100 or graph_hidden_size != 100 \
+                    or att_type not in ('concat_subsequently', 'concat_only', 'gated', 'mfn_only', 'lmf_only'):
+                raise NotImplementedError("graph_type='None': base_model='LSTM', modals='avl', D_e=graph_hidden_size=100, att_type in "
+                                          "concat_subsequently / concat_only / gated / mfn_only / lmf_only ('tfn_only' is not built)")
         elif base_model != 'LSTM' or sorted(modals) != ['a', 'l', 'v'] \
-                or graph_type not in ('GDF', 'relation') or av_using_lstm \
+                or graph_type not in ('GDF', 'GF', 'relation') or av_using_lstm \
                 or not (att_type in ('concat_subsequently', 'mfn') or (att_type == 'gated' and graph_type == 'relation')) \
                 or D_e != 100 or graph_hidden_size != 100 or not use_residue or (graph_type == 'relation' and use_GCN):
             raise NotImplementedError(
                 "mmdfn_b200 implements the MM-DFN hot path only: base_model='LSTM', multi_modal, modals='avl', "
-                "graph_type='GDF' (or 'relation'), att_type='concat_subsequently' or 'mfn' (or 'gated' with graph_type='relation'), "
+                "graph_type='GDF' (or 'relation' / 'None'), att_type='concat_subsequently' or 'mfn' (or 'gated' with graph_type='relation'), "
                 "D_e=graph_hidden_size=100, use_residue")
         self.base_model, self.avec, self.no_cuda, self.graph_type = base_model, avec, no_cuda, graph_type
         self.alpha, self.lamda, self.multiheads, self.graph_construct = alpha, lamda, multiheads, graph_construct
@@ -505,12 +512,18 @@ class DialogueGNNModel(nn.Module):
             self.graph_net_l = GraphNetwork(2 * D_e, n_classes, n_relations, max_seq_len, graph_hidden_size, dropout,
                                             self.no_cuda, self.use_GCN, self.return_feature)
             print("construct relation graph")
+        elif graph_type == 'None':
+            self.graph_net_a = nn.Linear(2 * D_e, graph_hidden_size)
+            self.graph_net_v = nn.Linear(2 * D_e, graph_hidden_size)
+            self.graph_net_l = nn.Linear(2 * D_e, graph_hidden_size)
+            print("construct Bi-LSTM")
         else:
             self.graph_model = MM_GCN(a_dim=2 * D_e, v_dim=2 * D_e, l_dim=2 * D_e, n_dim=2 * D_e, nlayers=Deep_GCN_nlayers,
                                       nhidden=graph_hidden_size, nclass=n_classes, dropout=self.dropout, lamda=self.lamda,
                                       alpha=self.alpha, variant=True, return_feature=self.return_feature,
                                       use_residue=self.use_residue, n_speakers=n_speakers, modals=self.modals,
-                                      use_speaker=self.use_speaker, use_modal=self.use_modal, reason_flag=self.reason_flag,
+                                      use_speaker=self.use_speaker, use_modal=self.use_modal,
+                                      reason_flag=self.reason_flag if graph_type == 'GDF' else False,      # 'GF': no fusion gate (code/model.py:944-950)
                                       modal_weight=self.modal_weight)
             print("construct " + self.graph_type)
         self.edge_type_mapping = {}
@@ -522,9 +535,14 @@ class DialogueGNNModel(nn.Module):
         self.dropout_ = nn.Dropout(self.dropout)
         # code/model.py:984-994: the gated fusion feeds 100 features per modality pair into the classifier, the memory
         # fusion network 3 x 100 hidden states + the 100-d memory
-        if att_type == 'mfn':
+        if att_type in ('mfn', 'mfn_only'):
             self.mfn = MFN()
             self.smax_fc = nn.Linear(400, n_classes)
+        elif att_type == 'lmf_only':
+            self.lmf = LMF()
+            self.smax_fc = nn.Linear(300, n_classes)
+        elif att_type == 'concat_only':
+            self.smax_fc = nn.Linear(900, n_classes)
         else:
             self.smax_fc = nn.Linear((100 if att_type == 'gated' else 300) * len(self.modals), n_classes)
 
@@ -534,7 +552,7 @@ class DialogueGNNModel(nn.Module):
     def forward(self, U, qmask, umask, seq_lengths, U_a=None, U_v=None, test_label=False, masks=None):
         """U = text (T,B,D_m), U_a = audio, U_v = visual, qmask (T,B,S) -> (log_prob (N,C), None x4).
         `masks` (tests only): injected uint8 keep-masks {'gru_l','gru_p','gcn':{...},'head'}."""
-        if (self.use_speaker or self.use_modal) and self.graph_type == 'GDF':
+        if (self.use_speaker or self.use_modal) and self.graph_type in ('GDF', 'GF'):
             raise NotImplementedError("use_speaker / use_modal are off on the MM-DFN path")
         if not U.is_cuda:
             raise ops.MMDFNError("DialogueGNNModel.forward needs CUDA tensors: the B200 path has no CPU fallback")
@@ -551,7 +569,7 @@ class DialogueGNNModel(nn.Module):
         # every dropout keep-mask of the step comes from one launch (same counter stream, same bits as separate draws):
         # text GRU, party GRU, head, and -- when the graph stack uses the same rate on the GDF path -- its three masks
         nseq_p = 3 * B * S if self.use_crn_speaker else 0
-        gcn = self.graph_model.graph_net if self.graph_type != 'relation' else None
+        gcn = self.graph_model.graph_net if self.graph_type not in ('relation', 'None') else None
         pool_gcn = (train_drop and gcn is not None and gcn.training and float(gcn.dropout) == p)
         pooled = None
         if train_drop:
@@ -599,6 +617,8 @@ class DialogueGNNModel(nn.Module):
         m_h = pooled[2] if train_drop else mk.get("head")
         if self.graph_type == 'relation':
             return self._forward_relation(X, E_l, qmask, geom, seq_lengths, umask, m_h, scale, mk.get("gated"))
+        if self.graph_type == 'None':
+            return self._forward_no_graph(X, geom, T, mk), None, None, None, None
         gm = mk.get("gcn") if masks is not None else None
         if pool_gcn:
             gm = {"x": pooled[3], "h0": pooled[4], "layers": pooled[5] if len(gcn.convs) > 0 else None}
@@ -609,6 +629,32 @@ class DialogueGNNModel(nn.Module):
         with ops.sink_key("head"):
             log_prob = ops.HeadFn.apply(F_, geom.N, m_h, scale, self.smax_fc.weight, self.smax_fc.bias)
         return log_prob, None, None, None, None
+
+    def _forward_no_graph(self, X, geom, T, mk):
+        """graph_type='None' (code/model.py:1338-1405): emotions_m = [graph_net_m(features_m) | features_m] (N, 300) per
+        modality -> fusion (concat / gated / MFN / LMF) -> dropout -> smax_fc -> log_softmax (no ReLU on this branch).
+        `mk` (tests only): {'gated': {'in': ...}, 'mfn': four masks, 'head': (N, F) keep mask of the final dropout}."""
+        N = geom.N
+        em = []
+        for m, net in enumerate((self.graph_net_a, self.graph_net_v, self.graph_net_l)):
+            x = X[m * N:(m + 1) * N]
+            em.append(torch.cat([ops.LinearFn.apply(x, net.weight, net.bias), x], dim=-1))
+        if self.att_type in ('concat_subsequently', 'concat_only'):
+            feat = torch.cat(em, dim=-1)
+        elif self.att_type == 'gated':
+            feat = self.gatedatt(em[0], em[1], em[2], self.modals, masks=(mk.get("gated") or {}).get("in"))
+        elif self.att_type == 'lmf_only':
+            feat = self.lmf(em[0], em[1], em[2])
+        else:                                                    # 'mfn_only': emotions_tmp = [l | a | v], padded per dialogue
+            x = ops.MFNPackFn.apply(torch.cat(em, dim=0), geom, T, (2, 0, 1))
+            feat = ops.MFNUnpadFn.apply(self.mfn(x, masks=mk.get("mfn")), geom)
+        p = float(self.dropout)
+        m_g = mk.get("head")
+        if m_g is None and self.training and p > 0 and not mk:
+            m_g = ops.make_mask((N, feat.shape[1]), p, feat.device)
+        if m_g is not None:
+            feat = ops.MaskScaleFn.apply(feat, m_g, 1.0 / (1.0 - p))
+        return ops.LogSoftmaxFn.apply(ops.LinearFn.apply(feat, self.smax_fc.weight, self.smax_fc.bias))
 
     def _forward_text_only(self, U, qmask, umask, seq_lengths, masks=None):
         """Single-stream `relation` model (code/model.py:1035-1036, 1176-1180, 1211-1212): linear_ -> 2-layer BiGRU ->
