@@ -299,6 +299,20 @@ int mmdfn_lmf_fuse_bwd(int N, int H, int O, int R, const float* const* h, const 
                        const float* fz, const float* dout, float* dfz, float* const* dh, float* const* dfactor, float* dw,
                        float* dbias, void* stream);
 
+/* ---- ☆ f4: tensor fusion network (TFN, code/model_fusion.py:123-211; att_type = 'tfn_only') ------------------------
+ * y1 = dropout([1,h_a] (x) [1,h_v] (x) [1,h_t]) W1^T + b1 with h_m (N, 100) from the three sub-network Linears and
+ * W1 (300, 101^3 = 1030301).  The 4 MB-per-row fusion tensor exists only for one chunk of mmdfn_tfn_chunk_rows() rows at a
+ * time (ws: mmdfn_tfn_ws_floats(N) floats); its dropout keep bits are a function of (seed, offset + n * 1030301 + e), the
+ * same in both passes (p = 0: none).  _bwd takes dy1 = d/d(pre-activation), overwrites dha / dhv / dht (N, 100) and db1
+ * (300), overwrites or (accumulate != 0) accumulates into dW1; d1: scratch of 3 N 101 floats. */
+int mmdfn_tfn_chunk_rows();
+long long mmdfn_tfn_ws_floats(int N);
+int mmdfn_tfn_fuse_fwd(int N, const float* ha, const float* hv, const float* ht, const float* W1, const float* b1, float p,
+                       unsigned long long seed, unsigned long long offset, float* y1, float* ws, void* stream);
+int mmdfn_tfn_fuse_bwd(int N, const float* ha, const float* hv, const float* ht, const float* W1, float p,
+                       unsigned long long seed, unsigned long long offset, const float* dy1, float* dha, float* dhv,
+                       float* dht, float* dW1, float* db1, int accumulate, float* d1, float* ws, void* stream);
+
 /* ---- k13 (☆ SURVEY 8f rank 3): nodal attention of the relation path's classifier head ---------------------------
  * Replaces attentive_node_features + MatchingAttention('general2') (code/model.py:614-645, 66-76) on the ragged node
  * rows: per dialogue b (rows dia_off[b]..dia_off[b+1]-1 of E, Q, O: (N, D), D <= 512)

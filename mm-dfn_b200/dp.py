@@ -39,6 +39,8 @@ def used_prefixes(model):
             pre.append("gatedatt.")
         if model.att_type == "lmf_only":
             pre.append("lmf.")
+        if model.att_type == "tfn_only":
+            pre.append("tfn.")
         return tuple(pre)
     if getattr(model, "graph_type", "GDF") == "relation":
         pre += ["graph_net_a.", "graph_net_v.", "graph_net_l.", "att_model.scalar."]

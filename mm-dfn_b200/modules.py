@@ -327,6 +327,44 @@ def simple_batch_graphify(features, lengths, no_cuda):
 # code/model.py:784-1407
 # ------------------------------------------------------------------------------------------------
 # ------------------------------------------------------------------------------------------------
+# code/model_fusion.py:123-211
+# ------------------------------------------------------------------------------------------------
+class TFN(nn.Module):
+    """Tensor fusion network (Zadeh et al., EMNLP 2017) as the reference builds it (code/model_fusion.py:128-165): the same
+    sub-modules in the same order (identical state_dict keys and seed-for-seed initial weights, incl. the 309 M-parameter
+    `post_fusion_layer_1`); forward(audio_x, video_x, text_x) with three (N, 300) inputs -> (N, output_dim) runs on the
+    CUDA path: sub-network Linears on mmdfn_gemm, the fusion tensor / its dropout / the first post-fusion layer in
+    mmdfn_tfn_fuse_fwd / _bwd (one row chunk of the 4 MB-per-row tensor at a time), ReLU, second layer, ReLU."""
+
+    def __init__(self, input_dims=(300, 300, 300), hidden_dims=(100, 100, 100), dropouts=0.4, post_fusion_dim=300, output_dim=300):
+        super().__init__()
+        if tuple(hidden_dims) != (100, 100, 100) or post_fusion_dim != 300:
+            raise NotImplementedError("TFN: hidden_dims=(100, 100, 100), post_fusion_dim=300 (the reference's defaults)")
+        self.audio_in, self.video_in, self.text_in = input_dims
+        self.audio_hidden, self.video_hidden, self.text_hidden = hidden_dims
+        self.post_fusion_dim = post_fusion_dim
+        self.post_fusion_prob = dropouts
+        self.audio_subnet = nn.Linear(self.audio_in, self.audio_hidden)
+        self.video_subnet = nn.Linear(self.video_in, self.video_hidden)
+        self.text_subnet = nn.Linear(self.text_in, self.text_hidden)
+        self.post_fusion_dropout = nn.Dropout(p=self.post_fusion_prob)
+        self.post_fusion_layer_1 = nn.Linear((self.text_hidden + 1) * (self.video_hidden + 1) * (self.audio_hidden + 1), self.post_fusion_dim)
+        self.post_fusion_layer_2 = nn.Linear(self.post_fusion_dim, output_dim)
+
+    def forward(self, audio_x, video_x, text_x):
+        if not audio_x.is_cuda:
+            raise ops.MMDFNError("TFN.forward needs CUDA tensors: the B200 path has no CPU fallback")
+        ha = ops.LinearFn.apply(audio_x, self.audio_subnet.weight, self.audio_subnet.bias)
+        hv = ops.LinearFn.apply(video_x, self.video_subnet.weight, self.video_subnet.bias)
+        ht = ops.LinearFn.apply(text_x, self.text_subnet.weight, self.text_subnet.bias)
+        p = float(self.post_fusion_dropout.p) if self.post_fusion_dropout.training else 0.0
+        y1 = ops.TFNFuseFn.apply(ha, hv, ht, self.post_fusion_layer_1.weight, self.post_fusion_layer_1.bias, p)
+        y1 = ops.ReluMaskFn.apply(y1, None, 1.0)
+        y2 = ops.LinearFn.apply(y1, self.post_fusion_layer_2.weight, self.post_fusion_layer_2.bias)
+        return ops.ReluMaskFn.apply(y2, None, 1.0)
+
+
+# ------------------------------------------------------------------------------------------------
 # code/model_fusion.py:214-310
 # ------------------------------------------------------------------------------------------------
 class LMF(nn.Module):
@@ -450,9 +488,9 @@ class DialogueGNNModel(nn.Module):
             # graph-free multimodal baselines (code/model.py:952-961, 1338-1405): per-modality Linear(200 -> 100) on the encoder
             # features, [that | features] per modality, one of the fusion blocks, dropout -> smax_fc -> log_softmax
             if base_model != 'LSTM' or sorted(modals) != ['a', 'l', 'v'] or av_using_lstm or D_e != 100 or graph_hidden_size != 100 \
-                    or att_type not in ('concat_subsequently', 'concat_only', 'gated', 'mfn_only', 'lmf_only'):
+                    or att_type not in ('concat_subsequently', 'concat_only', 'gated', 'mfn_only', 'tfn_only', 'lmf_only'):
                 raise NotImplementedError("graph_type='None': base_model='LSTM', modals='avl', D_e=graph_hidden_size=100, att_type in "
-                                          "concat_subsequently / concat_only / gated / mfn_only / lmf_only ('tfn_only' is not built)")
+                                          "concat_subsequently / concat_only / gated / mfn_only / tfn_only / lmf_only")
         elif base_model != 'LSTM' or sorted(modals) != ['a', 'l', 'v'] \
                 or graph_type not in ('GDF', 'GF', 'relation') or av_using_lstm \
                 or not (att_type in ('concat_subsequently', 'mfn') or (att_type == 'gated' and graph_type == 'relation')) \
@@ -538,6 +576,9 @@ class DialogueGNNModel(nn.Module):
         if att_type in ('mfn', 'mfn_only'):
             self.mfn = MFN()
             self.smax_fc = nn.Linear(400, n_classes)
+        elif att_type == 'tfn_only':
+            self.tfn = TFN()
+            self.smax_fc = nn.Linear(300, n_classes)
         elif att_type == 'lmf_only':
             self.lmf = LMF()
             self.smax_fc = nn.Linear(300, n_classes)
@@ -645,6 +686,8 @@ class DialogueGNNModel(nn.Module):
             feat = self.gatedatt(em[0], em[1], em[2], self.modals, masks=(mk.get("gated") or {}).get("in"))
         elif self.att_type == 'lmf_only':
             feat = self.lmf(em[0], em[1], em[2])
+        elif self.att_type == 'tfn_only':
+            feat = self.tfn(em[0], em[1], em[2])
         else:                                                    # 'mfn_only': emotions_tmp = [l | a | v], padded per dialogue
             x = ops.MFNPackFn.apply(torch.cat(em, dim=0), geom, T, (2, 0, 1))
             feat = ops.MFNUnpadFn.apply(self.mfn(x, masks=mk.get("mfn")), geom)

@@ -651,6 +651,48 @@ class LMFFuseFn(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------------
+# f4: tensor fusion network (TFN)
+# ---------------------------------------------------------------------------------------------
+class TFNFuseFn(torch.autograd.Function):
+    """y1 = dropout([1,h_a] (x) [1,h_v] (x) [1,h_t]) W1^T + b1 (code/model_fusion.py:186-205, before the ReLU); the fusion
+    tensor lives one row chunk at a time inside the call.  p > 0: keep bits from the counter-based generator (same counter
+    in forward and backward)."""
+
+    @staticmethod
+    def forward(ctx, ha, hv, ht, W1, b1, p):
+        hs = [_f32c(x) for x in (ha, hv, ht)]
+        W1, b1 = _f32c(W1), _f32c(b1)
+        N = hs[0].shape[0]
+        seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        offset = _mask_counter[0]
+        if p > 0:
+            if _STEP_STATE[0] is not None:
+                raise MMDFNError("TFN dropout inside a captured step is not supported (its counter base is a launch argument)")
+            _mask_counter[0] = (_mask_counter[0] + N * 1030301) & 0xFFFFFFFFFFFFFFFF
+        ws = _empty((query("mmdfn_tfn_ws_floats", N),), ha.device)
+        y1 = _empty((N, 300), ha.device)
+        call("mmdfn_tfn_fuse_fwd", N, ptr(hs[0]), ptr(hs[1]), ptr(hs[2]), ptr(W1), ptr(b1), float(p), seed, offset, ptr(y1), ptr(ws),
+             stream())
+        ctx.save_for_backward(*hs, W1)
+        ctx.cfg = (N, float(p), seed, offset)
+        return y1
+
+    @staticmethod
+    def backward(ctx, dy1):
+        ha, hv, ht, W1 = ctx.saved_tensors
+        N, p, seed, offset = ctx.cfg
+        dev = dy1.device
+        dy1 = _f32c(dy1)
+        dh = [_empty((N, 100), dev) for _ in range(3)]
+        dW1, db1 = _empty(tuple(W1.shape), dev), _empty((300,), dev)
+        d1 = _empty((max(3 * N * 101, 1),), dev)
+        ws = _empty((query("mmdfn_tfn_ws_floats", N),), dev)
+        call("mmdfn_tfn_fuse_bwd", N, ptr(ha), ptr(hv), ptr(ht), ptr(W1), p, seed, offset, ptr(dy1), ptr(dh[0]), ptr(dh[1]), ptr(dh[2]),
+             ptr(dW1), ptr(db1), 0, ptr(d1), ptr(ws), stream())
+        return dh[0], dh[1], dh[2], dW1, db1, None
+
+
+# ---------------------------------------------------------------------------------------------
 # k13 (f3): nodal attention of the relation path's classifier head
 # ---------------------------------------------------------------------------------------------
 class NodalGeom:

@@ -71,6 +71,25 @@ def test_no_graph_baselines_vs_oracle(att):
     assert {n for n, _ in used_parameters(m)} == {k for k, p in m.named_parameters() if p.grad is not None}
 
 
+def test_no_graph_tfn_only_runs_end_to_end():
+    """att_type='tfn_only' (code/model.py:1389-1390): the model-level wiring of the TFN block (the block itself is pinned to
+    the reference in tests/test_gpu_tfn.py): normalised log-probabilities, finite gradients for exactly the trainer's set."""
+    import mmdfn_b200 as mm
+    from mmdfn_b200.dp import used_parameters
+    lengths, S, C = [7, 12, 5], 2, 6
+    t, a, v, q, u, lab = O.synthetic_batch(lengths, 100, 40, 24, S, C, seed=41)
+    torch.manual_seed(3)
+    m = mm.DialogueGNNModel("LSTM", 100, 150, 150, 100, 100, 100, 100, n_speakers=S, max_seq_len=200, window_past=10,
+                            window_future=10, n_classes=C, dropout=0.0, graph_type="None", D_m_v=24, D_m_a=40, modals="avl",
+                            att_type="tfn_only", use_speaker=False, use_crn_speaker=True, speaker_weights="1-1-1").to(DEV).train()
+    lp = m(t.to(DEV), q.to(DEV), u.to(DEV), lengths, a.to(DEV), v.to(DEV))[0]
+    assert lp.shape == (sum(lengths), C) and float((lp.exp().sum(1) - 1).abs().max()) < 1e-5
+    mm.FocalLoss(gamma=1.0)(lp, lab.to(DEV)).backward()
+    got = {k for k, p in m.named_parameters() if p.grad is not None}
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+    assert {n for n, _ in used_parameters(m)} == got
+
+
 def test_graph_type_gf_is_gdf_without_the_fusion_gate():
     """graph_type='GF' (code/model.py:944-950): the same MM_GCN as 'GDF' built with reason_flag=False whatever the model's
     own flag says -- same logits as a 'GDF' model constructed with reason_flag=False and the same weights."""
