@@ -33,6 +33,15 @@ def used_prefixes(model):
     if getattr(model, "att_type", "") in ("mfn", "mfn_only"):
         # out_fc1 / out_fc2 of the memory fusion network are constructed but never used: no gradient, Adam skips them
         pre += ["mfn.lstm_", "mfn.att1_", "mfn.att2_", "mfn.gamma1_", "mfn.gamma2_"]
+    if getattr(model, "graph_type", "GDF") == "DeepGCN":
+        for n in "avl":
+            net = getattr(model, "graph_net_" + n)
+            pre += [f"graph_net_{n}.fcs.0.", f"graph_net_{n}.convs."]
+            if net.reason_flag and len(net.convs) > 0:
+                pre.append(f"graph_net_{n}.rnn.")
+        if model.att_type == "gated":
+            pre.append("gatedatt.")
+        return tuple(pre)
     if getattr(model, "graph_type", "GDF") == "None":
         pre += ["graph_net_a.", "graph_net_v.", "graph_net_l."]
         if model.att_type == "gated":

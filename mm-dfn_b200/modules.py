@@ -5,10 +5,14 @@ paths relative to the reference root) so that code/run_train_erc.py works unchan
 mm-dfn_b200/dropin first on sys.path.  Sub-modules are created in the reference's order with
 the same nn primitives, hence the same seed yields the same initial weights.
 
-Supported configuration (anything else raises NotImplementedError -- there is no fallback):
-base_model='LSTM', multi_modal=True, modals='avl', graph_type='GDF',
-att_type='concat_subsequently', av_using_lstm=False, with or without use_crn_speaker /
-reason_flag / use_residue=True."""
+Supported configurations (anything else raises NotImplementedError -- there is no fallback): base_model='LSTM',
+av_using_lstm=False, D_e = graph_hidden_size = 100, with or without use_crn_speaker / reason_flag, and
+  * multi_modal, modals='avl', graph_type 'GDF' (the MM-DFN path; att_type 'concat_subsequently' or 'mfn'), 'GF' (no
+    fusion gate), 'relation' (RGCN/GraphConv per modality; att_type also 'gated'), 'DeepGCN' (GCNII per modality;
+    'concat_subsequently' / 'gated' / 'mfn'), 'None' (graph-free baselines; 'concat_only' / 'lmf_only' / 'tfn_only' /
+    'mfn_only' / 'gated' / 'concat_subsequently');
+  * multi_modal=False (or an att_type outside the reference's multimodal list), graph_type='relation': the single-stream
+    DialogueGCN configuration with the nodal-attention head."""
 import math
 
 import torch
@@ -143,6 +147,68 @@ class GCNII_lyc(nn.Module):
                                         scale, self.fcs[0].weight, self.fcs[0].bias, self.rnn.weight_ih_l0,
                                         self.rnn.weight_hh_l0, self.rnn.bias_ih_l0, self.rnn.bias_hh_l0,
                                         *[c.weight for c in self.convs])
+
+
+# ------------------------------------------------------------------------------------------------
+# code/model_GCN.py:224-306
+# ------------------------------------------------------------------------------------------------
+class GCNII(nn.Module):
+    """The per-modality deep GCN of graph_type='DeepGCN' as the reference builds it (code/model_GCN.py:225-247: same
+    sub-modules in the same order).  forward(x, dia_len, qmask): x (N, 200) -> (N, 300) = [dropout(x) | dropout(z_K)] over
+    the uni-modal angular-similarity graph (:274-297) -- GCNII_lyc's layer loop without the in-loop dropout, one dropout
+    after it (:263-273).
+
+    The graph kernels work on the stacked three-modality layout with ONE weight set, so a single modality runs as
+    modality slot `m` of a stacked input whose cross-modal weights are zero (then the multimodal adjacency is exactly the
+    three uni-modal ones): `forward_slot` takes the stacked features and the shared adjacency -- the DeepGCN model calls it
+    once per modality network, paying the stack three times for the three weight sets --, `forward` stacks its input three
+    times.  An ablation path: correctness first."""
+
+    def __init__(self, nfeat, nlayers, nhidden, nclass, dropout, lamda, alpha, variant, return_feature, use_residue, new_graph=False,
+                 reason_flag=False):
+        super().__init__()
+        if (nfeat, nhidden) != (200, 100) or not variant or new_graph or not (return_feature and use_residue):
+            raise NotImplementedError("GCNII: nfeat=200, nhidden=100, variant=True, new_graph=False, return_feature=True, use_residue=True")
+        self.return_feature, self.use_residue, self.new_graph = return_feature, use_residue, new_graph
+        self.convs = nn.ModuleList([GraphConvolution(nhidden, nhidden, variant=variant) for _ in range(nlayers)])
+        self.fcs = nn.ModuleList([nn.Linear(nfeat, nhidden)])
+        self.act_fn = nn.ReLU()
+        self.dropout, self.alpha, self.lamda = dropout, alpha, lamda
+        self.rnn_layer = 1
+        self.rnn = nn.LSTM(nhidden, nhidden, self.rnn_layer)
+        self.reason_flag = reason_flag
+
+    def forward_slot(self, X, adj, slot, masks=None):
+        """X (3N, 200) stacked, adj: BlockAdj with zero cross-modal weights -> (N, 300) of modality slot `slot`.
+        `masks` (tests only): {'x': (3N,200), 'h0': (3N,100), 'out': (N,100)} uint8 keep masks."""
+        geom = adj.geom
+        N, n3, K = geom.N, 3 * geom.N, len(self.convs)
+        p = float(self.dropout)
+        mx = mh = mo = None
+        scale = 1.0
+        if masks is not None:
+            mx, mh, mo = masks.get("x"), masks.get("h0"), masks.get("out")
+            scale = 1.0 / (1.0 - p)
+        elif self.training and p > 0:
+            mx, mh, mo = ops.make_masks([(n3, 200), (n3, 100), (N, 100)], p, X.device)
+            scale = 1.0 / (1.0 - p)
+        F_ = ops.GCNStackFn.apply(X, adj.blk, adj.diag, geom, K, self.reason_flag, self.lamda, self.alpha, mx, mh, None, scale,
+                                  self.fcs[0].weight, self.fcs[0].bias, self.rnn.weight_ih_l0, self.rnn.weight_hh_l0,
+                                  self.rnn.bias_ih_l0, self.rnn.bias_hh_l0, *[c.weight for c in self.convs])
+        rows = F_[slot * N:(slot + 1) * N]
+        if mo is None:
+            return rows
+        return torch.cat([rows[:, :200], ops.MaskScaleFn.apply(rows[:, 200:].contiguous(), mo, scale)], dim=-1)
+
+    def forward(self, x, dia_len, qmask=None, masks=None):
+        if not x.is_cuda:
+            raise ops.MMDFNError("GCNII.forward needs CUDA tensors: the B200 path has no CPU fallback")
+        geom = _geom_of(dia_len, x.device)
+        X = torch.cat([x, x, x], dim=0)
+        blk, diag = ops.AdjFn.apply(X, geom, 0.0)
+        if masks is not None:
+            masks = {k: (torch.cat([v, v, v], dim=0) if k in ("x", "h0") else v) for k, v in masks.items()}
+        return self.forward_slot(X, BlockAdj(blk, diag, geom), 0, masks)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -492,8 +558,8 @@ class DialogueGNNModel(nn.Module):
                 raise NotImplementedError("graph_type='None': base_model='LSTM', modals='avl', D_e=graph_hidden_size=100, att_type in "
                                           "concat_subsequently / concat_only / gated / mfn_only / tfn_only / lmf_only")
         elif base_model != 'LSTM' or sorted(modals) != ['a', 'l', 'v'] \
-                or graph_type not in ('GDF', 'GF', 'relation') or av_using_lstm \
-                or not (att_type in ('concat_subsequently', 'mfn') or (att_type == 'gated' and graph_type == 'relation')) \
+                or graph_type not in ('GDF', 'GF', 'relation', 'DeepGCN') or av_using_lstm \
+                or not (att_type in ('concat_subsequently', 'mfn') or (att_type == 'gated' and graph_type in ('relation', 'DeepGCN'))) \
                 or D_e != 100 or graph_hidden_size != 100 or not use_residue or (graph_type == 'relation' and use_GCN):
             raise NotImplementedError(
                 "mmdfn_b200 implements the MM-DFN hot path only: base_model='LSTM', multi_modal, modals='avl', "
@@ -550,6 +616,13 @@ class DialogueGNNModel(nn.Module):
             self.graph_net_l = GraphNetwork(2 * D_e, n_classes, n_relations, max_seq_len, graph_hidden_size, dropout,
                                             self.no_cuda, self.use_GCN, self.return_feature)
             print("construct relation graph")
+        elif graph_type == 'DeepGCN':
+            # code/model.py:928-940: one GCNII per modality, lamda = 0.5, alpha = 0.1 whatever the model's own values
+            mk_net = lambda: GCNII(nfeat=2 * D_e, nlayers=Deep_GCN_nlayers, nhidden=graph_hidden_size, nclass=n_classes,
+                                   dropout=self.dropout, lamda=0.5, alpha=0.1, variant=True, return_feature=self.return_feature,
+                                   use_residue=self.use_residue, reason_flag=self.reason_flag)
+            self.graph_net_a, self.graph_net_v, self.graph_net_l = mk_net(), mk_net(), mk_net()
+            print("construct " + self.graph_type, "with", Deep_GCN_nlayers, "layers")
         elif graph_type == 'None':
             self.graph_net_a = nn.Linear(2 * D_e, graph_hidden_size)
             self.graph_net_v = nn.Linear(2 * D_e, graph_hidden_size)
@@ -610,7 +683,7 @@ class DialogueGNNModel(nn.Module):
         # every dropout keep-mask of the step comes from one launch (same counter stream, same bits as separate draws):
         # text GRU, party GRU, head, and -- when the graph stack uses the same rate on the GDF path -- its three masks
         nseq_p = 3 * B * S if self.use_crn_speaker else 0
-        gcn = self.graph_model.graph_net if self.graph_type not in ('relation', 'None') else None
+        gcn = self.graph_model.graph_net if self.graph_type in ('GDF', 'GF') else None
         pool_gcn = (train_drop and gcn is not None and gcn.training and float(gcn.dropout) == p)
         pooled = None
         if train_drop:
@@ -660,6 +733,8 @@ class DialogueGNNModel(nn.Module):
             return self._forward_relation(X, E_l, qmask, geom, seq_lengths, umask, m_h, scale, mk.get("gated"))
         if self.graph_type == 'None':
             return self._forward_no_graph(X, geom, T, mk), None, None, None, None
+        if self.graph_type == 'DeepGCN':
+            return self._forward_deep_gcn(X, geom, T, m_h, scale, mk), None, None, None, None
         gm = mk.get("gcn") if masks is not None else None
         if pool_gcn:
             gm = {"x": pooled[3], "h0": pooled[4], "layers": pooled[5] if len(gcn.convs) > 0 else None}
@@ -670,6 +745,30 @@ class DialogueGNNModel(nn.Module):
         with ops.sink_key("head"):
             log_prob = ops.HeadFn.apply(F_, geom.N, m_h, scale, self.smax_fc.weight, self.smax_fc.bias)
         return log_prob, None, None, None, None
+
+    def _forward_deep_gcn(self, X, geom, T, m_h, scale, mk):
+        """graph_type='DeepGCN' (code/model.py:1244-1293): one GCNII per modality over its own uni-modal graph -> fusion (concat /
+        gated / MFN) -> dropout -> ReLU -> smax_fc -> log_softmax.  The three uni-modal adjacencies are ONE call on the stacked
+        features with zero cross-modal weights.  `mk` (tests only): {'gcn_a' / 'gcn_v' / 'gcn_l': GCNII masks, 'gated': {...},
+        'mfn': [...], 'head': keep mask of the final dropout}."""
+        N = geom.N
+        blk, diag = ops.AdjFn.apply(X, geom, 0.0)
+        adj = BlockAdj(blk, diag, geom)
+        inject = bool(mk)
+        em = [net.forward_slot(X, adj, m, mk.get("gcn_" + n) if inject else None)
+              for m, (n, net) in enumerate((("a", self.graph_net_a), ("v", self.graph_net_v), ("l", self.graph_net_l)))]
+        if self.att_type == 'concat_subsequently':
+            with ops.sink_key("head"):
+                return ops.HeadFn.apply(torch.cat(em, dim=0), N, m_h, scale, self.smax_fc.weight, self.smax_fc.bias)
+        if self.att_type == 'mfn':
+            return self._mfn_head(torch.cat(em, dim=0), geom, T, (2, 0, 1), mk)
+        feat = self.gatedatt(em[0], em[1], em[2], self.modals, masks=(mk.get("gated") or {}).get("in"))
+        p = float(self.dropout)
+        m_g = mk.get("head")
+        if m_g is None and self.training and p > 0 and not inject:
+            m_g = ops.make_mask((N, feat.shape[1]), p, feat.device)
+        feat = ops.ReluMaskFn.apply(feat, m_g, 1.0 / (1.0 - p) if m_g is not None else 1.0)
+        return ops.LogSoftmaxFn.apply(ops.LinearFn.apply(feat, self.smax_fc.weight, self.smax_fc.bias))
 
     def _forward_no_graph(self, X, geom, T, mk):
         """graph_type='None' (code/model.py:1338-1405): emotions_m = [graph_net_m(features_m) | features_m] (N, 300) per

@@ -319,6 +319,26 @@ def gcnii_stack(x: Tensor, adj, P: Dict[str, Tensor], prefix: str, nlayers: int,
 
 
 # --------------------------------------------------------------------------------------
+# f4 (☆)  GCNII: the per-modality deep GCN of graph_type='DeepGCN'   code/model_GCN.py:224-306
+# --------------------------------------------------------------------------------------
+def gcnii(x: Tensor, dia_len: Sequence[int], P: Dict[str, Tensor], prefix: str, nlayers: int, lamda: float, alpha: float,
+          reason_flag: bool = False, masks: Optional[dict] = None) -> Tensor:
+    """``GCNII.forward`` with return_feature=True, use_residue=True, new_graph=False: the uni-modal angular-similarity
+    adjacency of ``GCNII.create_big_adj`` (:274-297: the in-modal block of the multimodal one, degree = row sum), then
+    the same layer loop as GCNII_lyc WITHOUT the in-loop dropout (:263-271) and ONE dropout after it (:273).
+    masks: {'x': (N,200), 'h0': (N,100), 'out': (N,100)} pre-scaled; None = identity."""
+    mk = dict(masks or {})
+    out_mask = mk.pop("out", None)
+    mk.pop("layer", None)
+    blocks, diags = adj_blocks([x], dia_len, 1.0)
+    adj = lambda z: adj_matmul_blocks(blocks, diags, dia_len, z, M=1)
+    F_ = gcnii_stack(x, adj, P, prefix, nlayers, lamda, alpha, reason_flag, True, mk)
+    if out_mask is not None:
+        F_ = torch.cat([F_[:, :200], F_[:, 200:] * out_mask], -1)
+    return F_
+
+
+# --------------------------------------------------------------------------------------
 # a5  MM_GCN.forward                                                 code/model_mm.py:77-120
 # --------------------------------------------------------------------------------------
 def mm_gcn(a: Tensor, v: Tensor, l: Tensor, dia_len: Sequence[int], P: Dict[str, Tensor], prefix: str,
