@@ -25,11 +25,12 @@ struct GcnLayerArgs {
   long long* dbg;
 };
 
-// x = hi + lo, hi = x rounded to tf32 (cvt.rna: one instruction), lo = the exact fp32 remainder
+// x = hi + lo, hi = x rounded to tf32 (nearest, ties away from zero), lo = the exact fp32 remainder.  The rounding is done
+// on the bit pattern (add half an ulp of the 13 dropped bits to the magnitude, clear them): the same values as
+// cvt.rna.tf32.f32 for finite inputs in two integer operations -- the conversion instruction expands to five with its
+// NaN / infinity handling, and the converter warps of these kernels are issue-bound.
 __device__ __forceinline__ void gl_split(float x, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
   lo = x - hi;
 }
 

@@ -193,9 +193,9 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 // x = hi + lo with hi = rna(x) (tf32, low 13 mantissa bits zero) and lo = x - hi exact in fp32; the tensor core
 // drops the low 13 bits of lo, leaving a relative error ~2^-21: a_hi*b_hi + a_lo*b_hi + a_hi*b_lo ~ fp32 product.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
+  // rna on the bit pattern: + half an ulp of the 13 dropped bits, clear them (= cvt.rna.tf32.f32 for finite x, in two
+  // integer operations instead of the five the conversion expands to with its NaN / infinity handling)
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
   lo = x - hi;
 }
 
