@@ -100,6 +100,16 @@ int mmdfn_bigru2_bwd_in(int in_dim, int T, int nseq, long long rows, const float
                         const float* const* w, const unsigned char* mask, float mask_scale, const float* y2,
                         const float* dy2, const float* ws_fwd, float* dx, int accumulate_dx, float* const* dw,
                         int dw_zeroed, float* ws, void* stream);
+/* the same backward in two calls that may run on different streams: _data = both recurrences, the layer-1 input gradient,
+   the scatter and dx (the step's dependency chain; also accumulates the bias gradients); _wgrad = the weight-gradient
+   contractions, reading the workspace the data part filled (the caller orders the two with an event). */
+int mmdfn_bigru2_bwd_data(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                          const float* const* w, const unsigned char* mask, float mask_scale, const float* y2,
+                          const float* dy2, const float* ws_fwd, float* dx, int accumulate_dx, float* const* dw,
+                          int dw_zeroed, float* ws, void* stream);
+int mmdfn_bigru2_bwd_wgrad(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                           const unsigned char* mask, const float* y2, const float* ws_fwd, float* const* dw,
+                           int dw_zeroed, float* ws, void* stream);
 
 /* ---- k3/k4: speaker-party partition + fused scatter/combine/ragged pack ------------------------
  * code/model.py:1070-1090, 1101-1121, 1134-1154 and simple_batch_graphify :553-565.

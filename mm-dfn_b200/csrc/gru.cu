@@ -460,8 +460,8 @@ extern "C" int mmdfn_bigru2_fwd_in(int in_dim, int T, int nseq, long long rows, 
 
 extern "C" long long mmdfn_bigru2_bwd_ws_floats(int T, int nseq, long long rows) {
   const i64 slots = (i64)T * nseq;
-  // dxg (slots*600) | dgh (slots*600) | dy1 (slots*200) | dG (rows*600)
-  return slots * (600 + 600 + 200) + rows * 600;
+  // dxg1 | dgh1 | dxg0 | dgh0 (slots*600 each) | dy1 (slots*200) | dG (rows*600)
+  return slots * (4 * 600 + 200) + rows * 600;
 }
 
 // One layer's weight gradients.  dgate_in: (in_rows, 600) gradient w.r.t. the input gates of the rows of `xin`
@@ -497,55 +497,91 @@ extern "C" int mmdfn_bigru2_bwd(int T, int nseq, long long rows, const float* x,
                              ws, stream);
 }
 
-extern "C" int mmdfn_bigru2_bwd_in(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
-                                   const float* const* w, const unsigned char* mask, float mask_scale, const float* y2,
-                                   const float* dy2, const float* ws_fwd, float* dx, int accumulate_dx,
-                                   float* const* dw, int dw_zeroed, float* ws, void* stream) {
+// Backward in two parts, so that a caller may run the second one on another stream: the DATA part (both recurrences, the
+// layer-1 input gradient between them, the scatter and the input gradient) is the dependency chain of the step; the
+// WEIGHT-GRADIENT part (five long contractions, ~45 % of the encoder's backward kernel time) only feeds the optimizer.
+// Workspace (mmdfn_bigru2_bwd_ws_floats): dxg1 | dgh1 | dxg0 | dgh0 (slots*600 each) | dy1 (slots*200) | dG (rows*600);
+// the data part fills it, the weight-gradient part reads it.
+struct GruBwdWs { float *dxg1, *dgh1, *dxg0, *dgh0, *dy1, *dG; };
+static GruBwdWs gru_bwd_ws(float* ws, i64 slots) {
+  GruBwdWs r;
+  r.dxg1 = ws;
+  r.dgh1 = r.dxg1 + slots * 600;
+  r.dxg0 = r.dgh1 + slots * 600;
+  r.dgh0 = r.dxg0 + slots * 600;
+  r.dy1 = r.dgh0 + slots * 600;
+  r.dG = r.dy1 + slots * 200;
+  return r;
+}
+
+extern "C" int mmdfn_bigru2_bwd_data(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                                     const float* const* w, const unsigned char* mask, float mask_scale, const float* y2,
+                                     const float* dy2, const float* ws_fwd, float* dx, int accumulate_dx,
+                                     float* const* dw, int dw_zeroed, float* ws, void* stream) {
   if (!x || !w || !y2 || !dy2 || !ws_fwd || !dw || !ws) return MMDFN_ENULL;
   if (in_dim <= 0) return MMDFN_EINVAL;
   if (!rowmap && rows != (i64)T * nseq) return MMDFN_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const i64 slots = (i64)T * nseq;
   if (slots == 0) return 0;
-  const float* xg1 = ws_fwd; (void)xg1;
   const float* y1 = ws_fwd + rows * 600;
   const float* y1d = y1 + slots * 200;
   const float* gates1 = y1d + slots * 200;
   const float* gates2 = gates1 + slots * 800 + slots * 600;
-  const float* l1in = mask ? y1d : y1;
-  float* dxg = ws;
-  float* dgh = dxg + slots * 600;
-  float* dy1 = dgh + slots * 600;
-  float* dG = dy1 + slots * 200;
-  const float wbeta = dw_zeroed ? 1.f : 0.f;
+  const GruBwdWs b = gru_bwd_ws(ws, slots);
   if (!dw_zeroed) {
     for (int i = 0; i < 16; i++) {
       if ((i & 3) >= 2) MMDFN_TRY(fill_zero(dw[i], 300 * sizeof(float), st));       // bias gradients are accumulated with atomics
     }
   }
   // ---- layer 1 ----
-  GruBwdArgs b{T, nseq, dy2, y2, gates2, {w[9], w[13]}, dxg, dgh, {dw[10], dw[14]}, {dw[11], dw[15]}};
-  MMDFN_TRY(launch_gru_bwd(b, st));
-  MMDFN_TRY(gru_layer_wgrads(T, nseq, slots, dxg, l1in, 200, dgh, y2, dw, 8, wbeta, st));
+  GruBwdArgs l1{T, nseq, dy2, y2, gates2, {w[9], w[13]}, b.dxg1, b.dgh1, {dw[10], dw[14]}, {dw[11], dw[15]}};
+  MMDFN_TRY(launch_gru_bwd(l1, st));
   // d(layer-1 input) = dgates_f W_ih_f + dgates_b W_ih_b: one contraction over the 600 gate columns
-  MMDFN_TRY(gemm_nn_kpair((int)slots, 200, 300, 300, dxg, 600, w[8], w[12], 200, 0.f, dy1, 200, st));
+  MMDFN_TRY(gemm_nn_kpair((int)slots, 200, 300, 300, b.dxg1, 600, w[8], w[12], 200, 0.f, b.dy1, 200, st));
   if (mask) {
-    MMDFN_TRY(mask_mul(dy1, mask, mask_scale, slots * 200, dy1, st));
+    MMDFN_TRY(mask_mul(b.dy1, mask, mask_scale, slots * 200, b.dy1, st));
   }
   // ---- layer 0 ----
-  GruBwdArgs a{T, nseq, dy1, y1, gates1, {w[1], w[5]}, dxg, dgh, {dw[2], dw[6]}, {dw[3], dw[7]}};
-  MMDFN_TRY(launch_gru_bwd(a, st));
-  const float* dgate_in = dxg;
+  GruBwdArgs l0{T, nseq, b.dy1, y1, gates1, {w[1], w[5]}, b.dxg0, b.dgh0, {dw[2], dw[6]}, {dw[3], dw[7]}};
+  MMDFN_TRY(launch_gru_bwd(l0, st));
+  const float* dgate_in = b.dxg0;
   if (rowmap) {
-    MMDFN_TRY(fill_zero(dG, (size_t)rows * 600 * sizeof(float), st));
-    scatter_rows_kernel<<<(unsigned)ceil_div64(slots, 4), dim3(32, 4), 0, st>>>(dxg, rowmap, slots, dG);
+    MMDFN_TRY(fill_zero(b.dG, (size_t)rows * 600 * sizeof(float), st));
+    scatter_rows_kernel<<<(unsigned)ceil_div64(slots, 4), dim3(32, 4), 0, st>>>(b.dxg0, rowmap, slots, b.dG);
     MMDFN_LAUNCH_CHECK();
-    dgate_in = dG;
+    dgate_in = b.dG;
   }
-  MMDFN_TRY(gru_layer_wgrads(T, nseq, rows, dgate_in, x, in_dim, dgh, y1, dw, 0, wbeta, st));
   if (dx) {
     const float beta = accumulate_dx ? 1.f : 0.f;
     MMDFN_TRY(gemm_nn_kpair((int)rows, in_dim, 300, 300, dgate_in, 600, w[0], w[4], in_dim, beta, dx, in_dim, st));
   }
   return 0;
+}
+
+extern "C" int mmdfn_bigru2_bwd_wgrad(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                                      const unsigned char* mask, const float* y2, const float* ws_fwd, float* const* dw,
+                                      int dw_zeroed, float* ws, void* stream) {
+  if (!x || !y2 || !ws_fwd || !dw || !ws) return MMDFN_ENULL;
+  if (in_dim <= 0) return MMDFN_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const i64 slots = (i64)T * nseq;
+  if (slots == 0) return 0;
+  const float* y1 = ws_fwd + rows * 600;
+  const float* y1d = y1 + slots * 200;
+  const float* l1in = mask ? y1d : y1;
+  const GruBwdWs b = gru_bwd_ws(ws, slots);
+  const float wbeta = dw_zeroed ? 1.f : 0.f;
+  MMDFN_TRY(gru_layer_wgrads(T, nseq, slots, b.dxg1, l1in, 200, b.dgh1, y2, dw, 8, wbeta, st));
+  MMDFN_TRY(gru_layer_wgrads(T, nseq, rows, rowmap ? b.dG : b.dxg0, x, in_dim, b.dgh0, y1, dw, 0, wbeta, st));
+  return 0;
+}
+
+extern "C" int mmdfn_bigru2_bwd_in(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                                   const float* const* w, const unsigned char* mask, float mask_scale, const float* y2,
+                                   const float* dy2, const float* ws_fwd, float* dx, int accumulate_dx,
+                                   float* const* dw, int dw_zeroed, float* ws, void* stream) {
+  MMDFN_TRY(mmdfn_bigru2_bwd_data(in_dim, T, nseq, rows, x, rowmap, w, mask, mask_scale, y2, dy2, ws_fwd, dx, accumulate_dx, dw,
+                                  dw_zeroed, ws, stream));
+  return mmdfn_bigru2_bwd_wgrad(in_dim, T, nseq, rows, x, rowmap, mask, y2, ws_fwd, dw, dw_zeroed, ws, stream);
 }

@@ -378,6 +378,30 @@ def plan_gru_tiles(T, n_a, n_b, sms=148):
     return pick
 
 
+def _wgrad_stream(device, cache={}):
+    key = str(device)
+    if key not in cache:
+        cache[key] = torch.cuda.Stream(device=device)
+    return cache[key]
+
+
+_WGRAD_JOIN = [False]
+
+
+def _join_wgrad_stream(device):
+    """once per backward pass: when autograd has run its last node, the stream that called backward() waits for the
+    weight-gradient stream (the optimizer / all-reduce / a captured graph's end come after that)"""
+    if _WGRAD_JOIN[0]:
+        return
+    _WGRAD_JOIN[0] = True
+
+    def join():
+        _WGRAD_JOIN[0] = False
+        torch.cuda.current_stream(device).wait_stream(_wgrad_stream(device))
+
+    torch.autograd.Variable._execution_engine.queue_callback(join)
+
+
 class BiGRU2Fn(torch.autograd.Function):
     """x (rows, in_dim) [+ rowmap (T,nseq) gather] -> y (T,nseq,200).  16 weights in GRU_KEYS order; in_dim = 200 on the
     MM-DFN path, the width of `linear_` in the text-only configuration."""
@@ -421,14 +445,32 @@ class BiGRU2Fn(torch.autograd.Function):
         tab, dtab = ptr_table(w), ptr_table(dw)
         call("mmdfn_gru_set_tile", ctx.tile)
         try:
-            call("mmdfn_bigru2_bwd_in", x.shape[1], T, nseq, rows, ptr(x), ptr(ctx.rowmap, torch.int32), tab, ptr(ctx.mask, U8),
+            # the dependency chain of the step: recurrences, the input gradients between and after them
+            call("mmdfn_bigru2_bwd_data", x.shape[1], T, nseq, rows, ptr(x), ptr(ctx.rowmap, torch.int32), tab, ptr(ctx.mask, U8),
                  ctx.mask_scale, ptr(y), ptr(dy), ptr(ws), ptr(dx), 0, dtab, 1, ptr(wsb), stream())
         finally:
             call("mmdfn_gru_set_tile", 0)
-        if direct:
-            _SINK[0].ready(ctx.sink_key)
-            return (dx, None, None, None, None, None, *([None] * 16))
-        return (dx, None, None, None, None, None, *dw)
+        dev = x.device
+        if not direct:
+            # gradients returned to autograd must be complete on the current stream
+            call("mmdfn_bigru2_bwd_wgrad", x.shape[1], T, nseq, rows, ptr(x), ptr(ctx.rowmap, torch.int32), ptr(ctx.mask, U8), ptr(y),
+                 ptr(ws), dtab, 1, ptr(wsb), stream())
+            return (dx, None, None, None, None, None, *dw)
+        # trainer mode (gradients go straight into the flat bucket): the weight-gradient contractions only feed the optimizer,
+        # so they run on their own stream behind an event, off the critical stream, and are joined when the backward pass
+        # ends (_join_wgrad_stream) -- before the all-reduce and Adam
+        cur, wst = torch.cuda.current_stream(dev), _wgrad_stream(dev)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        wst.wait_event(ev)
+        with torch.cuda.stream(wst):
+            call("mmdfn_bigru2_bwd_wgrad", x.shape[1], T, nseq, rows, ptr(x), ptr(ctx.rowmap, torch.int32), ptr(ctx.mask, U8), ptr(y),
+                 ptr(ws), dtab, 1, ptr(wsb), stream())
+        for t in (x, y, ws, wsb, flat):
+            t.record_stream(wst)
+        _join_wgrad_stream(dev)
+        _SINK[0].ready(ctx.sink_key)
+        return (dx, None, None, None, None, None, *([None] * 16))
 
 
 # ---------------------------------------------------------------------------------------------
