@@ -386,6 +386,7 @@ def _wgrad_stream(device, cache={}):
 
 
 _WGRAD_JOIN = [False]
+_WGRAD_KEEP = []
 
 
 def _join_wgrad_stream(device):
@@ -398,6 +399,7 @@ def _join_wgrad_stream(device):
     def join():
         _WGRAD_JOIN[0] = False
         torch.cuda.current_stream(device).wait_stream(_wgrad_stream(device))
+        _WGRAD_KEEP.clear()               # freed now: reused only by work ordered after this wait
 
     torch.autograd.Variable._execution_engine.queue_callback(join)
 
@@ -466,8 +468,9 @@ class BiGRU2Fn(torch.autograd.Function):
         with torch.cuda.stream(wst):
             call("mmdfn_bigru2_bwd_wgrad", x.shape[1], T, nseq, rows, ptr(x), ptr(ctx.rowmap, torch.int32), ptr(ctx.mask, U8), ptr(y),
                  ptr(ws), dtab, 1, ptr(wsb), stream())
-        for t in (x, y, ws, wsb, flat):
-            t.record_stream(wst)
+        # the buffers the other stream still reads stay referenced until the join (autograd drops this node's saved tensors as
+        # soon as it returns; record_stream would do, but its deferred frees made the caching allocator grow in eager loops)
+        _WGRAD_KEEP.append((x, y, ws, wsb, flat, dy))
         _join_wgrad_stream(dev)
         _SINK[0].ready(ctx.sink_key)
         return (dx, None, None, None, None, None, *([None] * 16))
