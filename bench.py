@@ -615,6 +615,21 @@ def main():
         launches = launches_per_step * K          # kernels inside the replayed graph (counted once at capture)
     inflight.clear()
     losses_seen.clear()
+    if os.environ.get("MMDFN_E2E_TRACE") == "1" and rank == 0:
+        # diagnostic (not part of any reported number): kernel / memcpy timeline of a few e2e steps -> stderr
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(6):
+                step_e2e(i)
+            drain_losses()
+            torch.cuda.synchronize()
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+        t0 = evs[0].time_range.start
+        for e in evs:
+            if "emcpy" in e.name or e.time_range.elapsed_us() > 150:
+                print("TRACE %9.1f us +%8.1f  %s" % (e.time_range.start - t0, e.time_range.elapsed_us(), e.name[:70]), file=sys.stderr)
+        inflight.clear()
+        losses_seen.clear()
     sec_e2e, _ = timed(step_e2e, K, finish=drain_losses)
     assert len(losses_seen) == K and all(np.isfinite(x) for x in losses_seen), "every e2e step's loss must reach the host"
     clocks = sampler.stop() if sampler else None
