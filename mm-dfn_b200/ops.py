@@ -289,7 +289,14 @@ class Proj3Fn(torch.autograd.Function):
         # and may start on its side stream while the audio / visual projections still run (event: Proj3Fn.text_ready)
         for m in (2, 0, 1):
             K = xs[m].shape[2]
-            call("mmdfn_gemm", 0, 1, rows, 200, K, 1.0, ptr(xs[m]), K, ptr(ws[m]), K, 0.0,
+            xa_, wa_, Kp = xs[m], ws[m], K
+            if K % 4 and rows * K >= (1 << 20):
+                # a feature width that is not a multiple of 4 floats (IEMOCAP audio: 1582) leaves rows off 16-byte
+                # alignment, which the TMA-fed tensor-core GEMM cannot take: zero-pad both operands' K (two copies, ~10 us)
+                Kp = (K + 3) // 4 * 4
+                xa_ = torch.nn.functional.pad(xs[m].reshape(rows, K), (0, Kp - K))
+                wa_ = torch.nn.functional.pad(ws[m], (0, Kp - K))
+            call("mmdfn_gemm", 0, 1, rows, 200, Kp, 1.0, ptr(xa_), Kp, ptr(wa_), Kp, 0.0,
                  U.data_ptr() + m * rows * 200 * 4, 200, ptr(bs[m]), 0, st)
             if m == 2:
                 Proj3Fn.text_ready = torch.cuda.Event()
