@@ -110,6 +110,16 @@ int mmdfn_bigru2_bwd_data(int in_dim, int T, int nseq, long long rows, const flo
 int mmdfn_bigru2_bwd_wgrad(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
                            const unsigned char* mask, const float* y2, const float* ws_fwd, float* const* dw,
                            int dw_zeroed, float* ws, void* stream);
+/* the two calls by layer (parts: bit 1 = layer 1, bit 0 = layer 0; 3 = the calls above): the layer-1 weight gradients need
+   only the layer-1 recurrence, so data(2), wgrad(2) [other stream], data(1), wgrad(1) [other stream] lets them run in the
+   shadow of the layer-0 recurrence, which occupies a fraction of the SMs. */
+int mmdfn_bigru2_bwd_data_part(int parts, int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                               const float* const* w, const unsigned char* mask, float mask_scale, const float* y2,
+                               const float* dy2, const float* ws_fwd, float* dx, int accumulate_dx, float* const* dw,
+                               int dw_zeroed, float* ws, void* stream);
+int mmdfn_bigru2_bwd_wgrad_part(int parts, int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                                const unsigned char* mask, const float* y2, const float* ws_fwd, float* const* dw,
+                                int dw_zeroed, float* ws, void* stream);
 
 /* ---- k3/k4: speaker-party partition + fused scatter/combine/ragged pack ------------------------
  * code/model.py:1070-1090, 1101-1121, 1134-1154 and simple_batch_graphify :553-565.

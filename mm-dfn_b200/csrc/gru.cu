@@ -514,12 +514,15 @@ static GruBwdWs gru_bwd_ws(float* ws, i64 slots) {
   return r;
 }
 
-extern "C" int mmdfn_bigru2_bwd_data(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
-                                     const float* const* w, const unsigned char* mask, float mask_scale, const float* y2,
-                                     const float* dy2, const float* ws_fwd, float* dx, int accumulate_dx,
-                                     float* const* dw, int dw_zeroed, float* ws, void* stream) {
+// parts: bit 1 = the layer-1 section (recurrence, input gradient of layer 1, its dropout mask), bit 0 = the layer-0 section
+// (recurrence, scatter, input gradient); a caller that wants the layer-1 weight gradients to overlap the layer-0 recurrence
+// calls data(2), wgrad(2) on another stream, data(1), wgrad(1).
+extern "C" int mmdfn_bigru2_bwd_data_part(int parts, int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                                          const float* const* w, const unsigned char* mask, float mask_scale, const float* y2,
+                                          const float* dy2, const float* ws_fwd, float* dx, int accumulate_dx,
+                                          float* const* dw, int dw_zeroed, float* ws, void* stream) {
   if (!x || !w || !y2 || !dy2 || !ws_fwd || !dw || !ws) return MMDFN_ENULL;
-  if (in_dim <= 0) return MMDFN_EINVAL;
+  if (in_dim <= 0 || (parts & ~3) || !parts) return MMDFN_EINVAL;
   if (!rowmap && rows != (i64)T * nseq) return MMDFN_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const i64 slots = (i64)T * nseq;
@@ -529,41 +532,53 @@ extern "C" int mmdfn_bigru2_bwd_data(int in_dim, int T, int nseq, long long rows
   const float* gates1 = y1d + slots * 200;
   const float* gates2 = gates1 + slots * 800 + slots * 600;
   const GruBwdWs b = gru_bwd_ws(ws, slots);
-  if (!dw_zeroed) {
-    for (int i = 0; i < 16; i++) {
-      if ((i & 3) >= 2) MMDFN_TRY(fill_zero(dw[i], 300 * sizeof(float), st));       // bias gradients are accumulated with atomics
+  if (parts & 2) {
+    if (!dw_zeroed) {
+      for (int i = 0; i < 16; i++) {
+        if ((i & 3) >= 2) MMDFN_TRY(fill_zero(dw[i], 300 * sizeof(float), st));     // bias gradients are accumulated with atomics
+      }
+    }
+    // ---- layer 1 ----
+    GruBwdArgs l1{T, nseq, dy2, y2, gates2, {w[9], w[13]}, b.dxg1, b.dgh1, {dw[10], dw[14]}, {dw[11], dw[15]}};
+    MMDFN_TRY(launch_gru_bwd(l1, st));
+    // d(layer-1 input) = dgates_f W_ih_f + dgates_b W_ih_b: one contraction over the 600 gate columns
+    MMDFN_TRY(gemm_nn_kpair((int)slots, 200, 300, 300, b.dxg1, 600, w[8], w[12], 200, 0.f, b.dy1, 200, st));
+    if (mask) {
+      MMDFN_TRY(mask_mul(b.dy1, mask, mask_scale, slots * 200, b.dy1, st));
     }
   }
-  // ---- layer 1 ----
-  GruBwdArgs l1{T, nseq, dy2, y2, gates2, {w[9], w[13]}, b.dxg1, b.dgh1, {dw[10], dw[14]}, {dw[11], dw[15]}};
-  MMDFN_TRY(launch_gru_bwd(l1, st));
-  // d(layer-1 input) = dgates_f W_ih_f + dgates_b W_ih_b: one contraction over the 600 gate columns
-  MMDFN_TRY(gemm_nn_kpair((int)slots, 200, 300, 300, b.dxg1, 600, w[8], w[12], 200, 0.f, b.dy1, 200, st));
-  if (mask) {
-    MMDFN_TRY(mask_mul(b.dy1, mask, mask_scale, slots * 200, b.dy1, st));
-  }
-  // ---- layer 0 ----
-  GruBwdArgs l0{T, nseq, b.dy1, y1, gates1, {w[1], w[5]}, b.dxg0, b.dgh0, {dw[2], dw[6]}, {dw[3], dw[7]}};
-  MMDFN_TRY(launch_gru_bwd(l0, st));
-  const float* dgate_in = b.dxg0;
-  if (rowmap) {
-    MMDFN_TRY(fill_zero(b.dG, (size_t)rows * 600 * sizeof(float), st));
-    scatter_rows_kernel<<<(unsigned)ceil_div64(slots, 4), dim3(32, 4), 0, st>>>(b.dxg0, rowmap, slots, b.dG);
-    MMDFN_LAUNCH_CHECK();
-    dgate_in = b.dG;
-  }
-  if (dx) {
-    const float beta = accumulate_dx ? 1.f : 0.f;
-    MMDFN_TRY(gemm_nn_kpair((int)rows, in_dim, 300, 300, dgate_in, 600, w[0], w[4], in_dim, beta, dx, in_dim, st));
+  if (parts & 1) {
+    // ---- layer 0 ----
+    GruBwdArgs l0{T, nseq, b.dy1, y1, gates1, {w[1], w[5]}, b.dxg0, b.dgh0, {dw[2], dw[6]}, {dw[3], dw[7]}};
+    MMDFN_TRY(launch_gru_bwd(l0, st));
+    const float* dgate_in = b.dxg0;
+    if (rowmap) {
+      MMDFN_TRY(fill_zero(b.dG, (size_t)rows * 600 * sizeof(float), st));
+      scatter_rows_kernel<<<(unsigned)ceil_div64(slots, 4), dim3(32, 4), 0, st>>>(b.dxg0, rowmap, slots, b.dG);
+      MMDFN_LAUNCH_CHECK();
+      dgate_in = b.dG;
+    }
+    if (dx) {
+      const float beta = accumulate_dx ? 1.f : 0.f;
+      MMDFN_TRY(gemm_nn_kpair((int)rows, in_dim, 300, 300, dgate_in, 600, w[0], w[4], in_dim, beta, dx, in_dim, st));
+    }
   }
   return 0;
 }
 
-extern "C" int mmdfn_bigru2_bwd_wgrad(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
-                                      const unsigned char* mask, const float* y2, const float* ws_fwd, float* const* dw,
-                                      int dw_zeroed, float* ws, void* stream) {
+extern "C" int mmdfn_bigru2_bwd_data(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                                     const float* const* w, const unsigned char* mask, float mask_scale, const float* y2,
+                                     const float* dy2, const float* ws_fwd, float* dx, int accumulate_dx,
+                                     float* const* dw, int dw_zeroed, float* ws, void* stream) {
+  return mmdfn_bigru2_bwd_data_part(3, in_dim, T, nseq, rows, x, rowmap, w, mask, mask_scale, y2, dy2, ws_fwd, dx, accumulate_dx, dw,
+                                    dw_zeroed, ws, stream);
+}
+
+extern "C" int mmdfn_bigru2_bwd_wgrad_part(int parts, int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                                           const unsigned char* mask, const float* y2, const float* ws_fwd, float* const* dw,
+                                           int dw_zeroed, float* ws, void* stream) {
   if (!x || !y2 || !ws_fwd || !dw || !ws) return MMDFN_ENULL;
-  if (in_dim <= 0) return MMDFN_EINVAL;
+  if (in_dim <= 0 || (parts & ~3) || !parts) return MMDFN_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const i64 slots = (i64)T * nseq;
   if (slots == 0) return 0;
@@ -572,9 +587,15 @@ extern "C" int mmdfn_bigru2_bwd_wgrad(int in_dim, int T, int nseq, long long row
   const float* l1in = mask ? y1d : y1;
   const GruBwdWs b = gru_bwd_ws(ws, slots);
   const float wbeta = dw_zeroed ? 1.f : 0.f;
-  MMDFN_TRY(gru_layer_wgrads(T, nseq, slots, b.dxg1, l1in, 200, b.dgh1, y2, dw, 8, wbeta, st));
-  MMDFN_TRY(gru_layer_wgrads(T, nseq, rows, rowmap ? b.dG : b.dxg0, x, in_dim, b.dgh0, y1, dw, 0, wbeta, st));
+  if (parts & 2) MMDFN_TRY(gru_layer_wgrads(T, nseq, slots, b.dxg1, l1in, 200, b.dgh1, y2, dw, 8, wbeta, st));
+  if (parts & 1) MMDFN_TRY(gru_layer_wgrads(T, nseq, rows, rowmap ? b.dG : b.dxg0, x, in_dim, b.dgh0, y1, dw, 0, wbeta, st));
   return 0;
+}
+
+extern "C" int mmdfn_bigru2_bwd_wgrad(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,
+                                      const unsigned char* mask, const float* y2, const float* ws_fwd, float* const* dw,
+                                      int dw_zeroed, float* ws, void* stream) {
+  return mmdfn_bigru2_bwd_wgrad_part(3, in_dim, T, nseq, rows, x, rowmap, mask, y2, ws_fwd, dw, dw_zeroed, ws, stream);
 }
 
 extern "C" int mmdfn_bigru2_bwd_in(int in_dim, int T, int nseq, long long rows, const float* x, const int* rowmap,

@@ -5,6 +5,7 @@ step of the hot path is a kernel of libmmdfn_b200.so.  Nothing here falls back t
 ops or to the CPU."""
 import ctypes
 import itertools
+import os
 
 import torch
 
@@ -385,27 +386,38 @@ def plan_gru_tiles(T, n_a, n_b, sms=148):
     return pick
 
 
-def _wgrad_stream(device, cache={}):
-    key = str(device)
+def _wgrad_stream(device, idx=0, cache={}):
+    key = (str(device), idx)
     if key not in cache:
         cache[key] = torch.cuda.Stream(device=device)
     return cache[key]
 
 
+# Where the trainer-mode weight-gradient contractions of the encoders run (measured at the bench shard, whole-step graph):
+# 0: one stream for all of them -- its chain of 12 GEMMs was the tail of the step (2.105 ms);
+# 1: one stream per encoder call, the two chains side by side (2.067 ms) -- the default;
+# 2: as 1, and the layer-1 contractions are enqueued right behind the layer-1 recurrence (2.071 ms: the two concurrent
+#    recurrences hold 144 of the 148 SMs, so nothing runs in their shadow and the early GEMMs only delay the layer-0 launch)
+_WGRAD_MODE = [int(os.environ.get("MMDFN_WGRAD_MODE", "1"))]
 _WGRAD_JOIN = [False]
 _WGRAD_KEEP = []
+_WGRAD_NEXT = [0]
+_WGRAD_NSTREAMS = 2
 
 
 def _join_wgrad_stream(device):
     """once per backward pass: when autograd has run its last node, the stream that called backward() waits for the
-    weight-gradient stream (the optimizer / all-reduce / a captured graph's end come after that)"""
+    weight-gradient streams (the optimizer / all-reduce / a captured graph's end come after that)"""
     if _WGRAD_JOIN[0]:
         return
     _WGRAD_JOIN[0] = True
 
     def join():
         _WGRAD_JOIN[0] = False
-        torch.cuda.current_stream(device).wait_stream(_wgrad_stream(device))
+        cur = torch.cuda.current_stream(device)
+        for i in range(min(_WGRAD_NEXT[0], _WGRAD_NSTREAMS)):      # only the streams this pass used (a captured step may
+            cur.wait_stream(_wgrad_stream(device, i))               # not wait for a stream outside its capture)
+        _WGRAD_NEXT[0] = 0
         _WGRAD_KEEP.clear()               # freed now: reused only by work ordered after this wait
 
     torch.autograd.Variable._execution_engine.queue_callback(join)
@@ -452,29 +464,50 @@ class BiGRU2Fn(torch.autograd.Function):
             off += n
         wsb = _empty((query("mmdfn_bigru2_bwd_ws_floats", T, nseq, rows),), x.device)
         tab, dtab = ptr_table(w), ptr_table(dw)
-        call("mmdfn_gru_set_tile", ctx.tile)
-        try:
-            # the dependency chain of the step: recurrences, the input gradients between and after them
-            call("mmdfn_bigru2_bwd_data", x.shape[1], T, nseq, rows, ptr(x), ptr(ctx.rowmap, torch.int32), tab, ptr(ctx.mask, U8),
-                 ctx.mask_scale, ptr(y), ptr(dy), ptr(ws), ptr(dx), 0, dtab, 1, ptr(wsb), stream())
-        finally:
-            call("mmdfn_gru_set_tile", 0)
+        xd = x.shape[1]
+        rm, mk = ptr(ctx.rowmap, torch.int32), ptr(ctx.mask, U8)
         dev = x.device
+
+        def data(parts):
+            # the dependency chain of the step: recurrences, the input gradients between and after them
+            call("mmdfn_gru_set_tile", ctx.tile)
+            try:
+                call("mmdfn_bigru2_bwd_data_part", parts, xd, T, nseq, rows, ptr(x), rm, tab, mk, ctx.mask_scale, ptr(y), ptr(dy),
+                     ptr(ws), ptr(dx), 0, dtab, 1, ptr(wsb), stream())
+            finally:
+                call("mmdfn_gru_set_tile", 0)
+
+        def wgrad(parts):
+            call("mmdfn_bigru2_bwd_wgrad_part", parts, xd, T, nseq, rows, ptr(x), rm, mk, ptr(y), ptr(ws), dtab, 1, ptr(wsb), stream())
+
         if not direct:
             # gradients returned to autograd must be complete on the current stream
-            call("mmdfn_bigru2_bwd_wgrad", x.shape[1], T, nseq, rows, ptr(x), ptr(ctx.rowmap, torch.int32), ptr(ctx.mask, U8), ptr(y),
-                 ptr(ws), dtab, 1, ptr(wsb), stream())
+            data(3)
+            wgrad(3)
             return (dx, None, None, None, None, None, *dw)
         # trainer mode (gradients go straight into the flat bucket): the weight-gradient contractions only feed the optimizer,
         # so they run on their own stream behind an event, off the critical stream, and are joined when the backward pass
         # ends (_join_wgrad_stream) -- before the all-reduce and Adam
-        cur, wst = torch.cuda.current_stream(dev), _wgrad_stream(dev)
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        wst.wait_event(ev)
-        with torch.cuda.stream(wst):
-            call("mmdfn_bigru2_bwd_wgrad", x.shape[1], T, nseq, rows, ptr(x), ptr(ctx.rowmap, torch.int32), ptr(ctx.mask, U8), ptr(y),
-                 ptr(ws), dtab, 1, ptr(wsb), stream())
+        mode = _WGRAD_MODE[0]
+        cur = torch.cuda.current_stream(dev)
+        wst = _wgrad_stream(dev, _WGRAD_NEXT[0] % _WGRAD_NSTREAMS if mode else 0)
+        _WGRAD_NEXT[0] += 1 if mode or not _WGRAD_NEXT[0] else 0
+
+        def wgrad_behind(parts):
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            wst.wait_event(ev)
+            with torch.cuda.stream(wst):
+                wgrad(parts)
+
+        if mode >= 2:
+            data(2)
+            wgrad_behind(2)
+            data(1)
+            wgrad_behind(1)
+        else:
+            data(3)
+            wgrad_behind(3)
         # the buffers the other stream still reads stay referenced until the join (autograd drops this node's saved tensors as
         # soon as it returns; record_stream would do, but its deferred frees made the caching allocator grow in eager loops)
         _WGRAD_KEEP.append((x, y, ws, wsb, flat, dy))

@@ -1,4 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -k "golden or model or parity or proj or real" > gpurun_out/r2t_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/r2t_tests.log
-timeout 600 python bench.py --steps 30 --warmup 5 --workload c2 > gpurun_out/r2m_bench_c2.json 2> gpurun_out/r2t_bench.err; echo "bench rc=$?"; cut -c1-230 gpurun_out/r2m_bench_c2.json
+for m in 1 2; do
+MMDFN_WGRAD_MODE=$m timeout 200 python tools/step_profile.py --graph > gpurun_out/r2t_prof_m$m.log 2>&1; echo "rc=$?"; tail -12 gpurun_out/r2t_prof_m$m.log; cp gpurun_out/step_timeline.txt gpurun_out/r2t_timeline_m$m.txt
+done
+rm -f gpurun_out/step_trace.json

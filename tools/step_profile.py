@@ -86,4 +86,5 @@ print("GPU busy (any stream) %.1f us of %.1f us span; %d gaps, total gap %.1f us
 print("largest gaps (us @offset):", sorted(gaps, reverse=True)[:8])
 with open(os.path.join(ROOT, "gpurun_out", "step_timeline.txt"), "w") as f:
     for e in last:
-        f.write("%9.1f %8.1f  s%-3s %s\n" % (e["ts"] - t0, e["dur"], e["args"].get("stream"), e["name"][:100]))
+        g = e["args"].get("grid", [0, 0, 0])
+        f.write("%9.1f %8.1f  s%-3s g%-5d %s\n" % (e["ts"] - t0, e["dur"], e["args"].get("stream"), g[0] * g[1] * g[2], e["name"][:90]))
