@@ -97,7 +97,10 @@ int gemm(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, i64
   if (ta && tb) return MMDFN_EINVAL;
   // large contractions run on the tensor cores (tcgen05 kind::tf32, 3-term split: fp32-level accuracy);
   // small ones stay on the FFMA tile kernel, whose prologue is cheaper than a TMEM allocation
-  if (2.0 * (double)M * (double)N * (double)K >= 1.8e8)
+  // (long TN contractions -- weight gradients -- earlier: the split-K FFMA kernel takes 33 us for the text projection's
+  // 200 x 100 x 3200 weight gradient, the tensor-core kernel ~12 us for 300 x 100 x 3168)
+  const double tc_min = (ta && K >= 2048) ? 1.0e8 : 1.8e8;
+  if (2.0 * (double)M * (double)N * (double)K >= tc_min)
     return umma_gemm(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act, st);
   GemmArgs p{A, lda, B, ldb, C, ldc, bias, M, N, K, alpha, beta, act, 1};
   // 128 x 64 tiles (8 x 4 per thread) only when even they give every SM several CTAs; otherwise 64 x 64 tiles: twice the

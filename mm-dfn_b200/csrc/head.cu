@@ -213,26 +213,45 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(int N, int C, const flo
 }
 
 // loss = (mean|sum)_n -(1-pt)^gamma * alpha[y] * lp[n,y],  pt = exp(lp[n,y]) (no gradient through pt)
-__global__ void focal_fwd_kernel(int N, int C, const float* __restrict__ lp, const long long* __restrict__ target,
-                                 const float* __restrict__ alpha, float gamma, float norm, float* __restrict__ loss) {
-  __shared__ float red[8];
-  float v = 0.f;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < N) {
-    const long long y = target[n];
-    const float l = lp[(i64)n * C + y];
-    const float a = alpha ? alpha[y] : 1.f;
-    const float w = gamma == 0.f ? 1.f : powf(1.f - expf(l), gamma);
-    v = -w * a * l * norm;
-  }
+__device__ __forceinline__ float focal_term(int n, int C, const float* __restrict__ lp, const long long* __restrict__ target,
+                                            const float* __restrict__ alpha, float gamma, float norm) {
+  const long long y = target[n];
+  const float l = lp[(i64)n * C + y];
+  const float a = alpha ? alpha[y] : 1.f;
+  const float w = gamma == 0.f ? 1.f : powf(1.f - expf(l), gamma);
+  return -w * a * l * norm;
+}
+
+__device__ __forceinline__ float focal_block_sum(float v, float* red) {
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-    v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(loss, v);
-  }
+  v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+  return warp_sum(v);                                      // valid in warp 0
+}
+
+__global__ void focal_fwd_kernel(int N, int C, const float* __restrict__ lp, const long long* __restrict__ target,
+                                 const float* __restrict__ alpha, float gamma, float norm, float* __restrict__ loss) {
+  __shared__ float red[32];
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const float v = focal_block_sum(n < N ? focal_term(n, C, lp, target, alpha, gamma, norm) : 0.f, red);
+  if (threadIdx.x == 0) atomicAdd(loss, v);
+}
+
+// Up to FOCAL_ONE_MAX rows: ONE block that WRITES the loss -- no zero-fill before it (in a replayed CUDA graph the 4-byte
+// memset node ahead of the atomics version cost 15 us of dependency latency on the step's critical chain, far more than
+// the kernel) and a fixed summation order.
+constexpr int FOCAL_ONE_MAX = 32768;
+__global__ void __launch_bounds__(1024) focal_fwd_one_kernel(int N, int C, const float* __restrict__ lp,
+                                                             const long long* __restrict__ target,
+                                                             const float* __restrict__ alpha, float gamma, float norm,
+                                                             float* __restrict__ loss) {
+  __shared__ float red[32];
+  float v = 0.f;
+#pragma unroll 4
+  for (int n = threadIdx.x; n < N; n += 1024) v += focal_term(n, C, lp, target, alpha, gamma, norm);
+  v = focal_block_sum(v, red);
+  if (threadIdx.x == 0) *loss = v;
 }
 
 __global__ void focal_bwd_kernel(int N, int C, const float* __restrict__ lp, const long long* __restrict__ target,
@@ -411,10 +430,14 @@ extern "C" int mmdfn_focal_loss_fwd(int N, int C, const float* log_prob, const l
                                     float gamma, int size_average, float* loss, void* stream) {
   if (!log_prob || !target || !loss) return MMDFN_ENULL;
   cudaStream_t st = (cudaStream_t)stream;
-  MMDFN_TRY(fill_zero(loss, sizeof(float), st));
-  if (N <= 0) return 0;
+  if (N <= 0) return fill_zero(loss, sizeof(float), st);
   const float norm = size_average ? 1.0f / (float)N : 1.0f;
-  focal_fwd_kernel<<<ceil_div(N, 256), 256, 0, st>>>(N, C, log_prob, target, alpha, gamma, norm, loss);
+  if (N <= FOCAL_ONE_MAX) {
+    focal_fwd_one_kernel<<<1, 1024, 0, st>>>(N, C, log_prob, target, alpha, gamma, norm, loss);
+  } else {
+    MMDFN_TRY(fill_zero(loss, sizeof(float), st));
+    focal_fwd_kernel<<<ceil_div(N, 256), 256, 0, st>>>(N, C, log_prob, target, alpha, gamma, norm, loss);
+  }
   MMDFN_LAUNCH_CHECK();
   return 0;
 }

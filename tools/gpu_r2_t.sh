@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-for m in 1 2; do
-MMDFN_WGRAD_MODE=$m timeout 200 python tools/step_profile.py --graph > gpurun_out/r2t_prof_m$m.log 2>&1; echo "rc=$?"; tail -12 gpurun_out/r2t_prof_m$m.log; cp gpurun_out/step_timeline.txt gpurun_out/r2t_timeline_m$m.txt
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/r2t_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r2t_tests.log
+for i in 1 2; do
+timeout 120 python bench.py --steps 60 --warmup 8 --no-cpu-baseline > gpurun_out/r2t_bench_$i.json 2> gpurun_out/r2t_bench.err; echo "bench rc=$?"; cut -c1-200 gpurun_out/r2t_bench_$i.json
 done
-rm -f gpurun_out/step_trace.json

@@ -51,7 +51,8 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         torch.cuda.synchronize()
 out = os.path.join(ROOT, "gpurun_out", "step_trace.json")
 prof.export_chrome_trace(out)
-ev = [e for e in json.load(open(out))["traceEvents"] if e.get("cat") == "kernel"]
+allev = json.load(open(out))["traceEvents"]
+ev = [e for e in allev if e.get("cat") == "kernel"]
 ev.sort(key=lambda e: e["ts"])
 # keep the last step: kernels after the (NSTEP-1)th adam kernel
 adam = [i for i, e in enumerate(ev) if "adam_kernel" in e["name"] or "adam_dev_kernel" in e["name"]]
@@ -88,3 +89,13 @@ with open(os.path.join(ROOT, "gpurun_out", "step_timeline.txt"), "w") as f:
     for e in last:
         g = e["args"].get("grid", [0, 0, 0])
         f.write("%9.1f %8.1f  s%-3s g%-5d %s\n" % (e["ts"] - t0, e["dur"], e["args"].get("stream"), g[0] * g[1] * g[2], e["name"][:90]))
+
+# what sits in the largest gap: every device-side trace event (any category) that overlaps it
+if gaps:
+    g, off = max(gaps)
+    lo, hi = t0 + off - 1.0, t0 + off + g + 1.0
+    print("events overlapping the largest gap (%.1f us @%.1f):" % (g, off))
+    for e in allev:
+        if e.get("ph") == "X" and e.get("cat") not in ("cpu_op", "python_function", "user_annotation", "cuda_runtime", "cuda_driver") \
+                and e["ts"] < hi and e["ts"] + e.get("dur", 0) > lo:
+            print("   %-14s %9.1f %7.1f  %s" % (e.get("cat"), e["ts"] - t0, e.get("dur", 0), e["name"][:80]))
